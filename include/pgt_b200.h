@@ -1,0 +1,162 @@
+/* pgt_b200.h — C ABI of libpgt_b200.so: the hand-written sm_100a kernels behind
+ * PGTFormer.forward.
+ *
+ * The reference (kepengxu/PGTFormer) exposes a Python class and no FFI; these
+ * entry points are what a `torch.ops`/ctypes binding for the hot path would bind.  Each entry
+ * cites the reference code it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *  - every function returns 0 (PGT_OK) or a negative pgt_status; it never throws, never
+ *    synchronises the device and never allocates caller-visible memory;
+ *  - all pointers are DEVICE pointers unless stated otherwise; `stream` is a cudaStream_t;
+ *  - activations are channels-last: a feature map is [F, H, W, C] (F = clips*3 frames) with an
+ *    explicit row stride `ld*` in ELEMENTS (so a kernel can read/write a channel slice of a wider
+ *    buffer); token matrices are [T, C] row-major.  bf16 unless a `*_dtype` argument says fp32;
+ *  - weights are pre-packed once at load time (pgtformer_b200/engine.py): linear [N, K] bf16 row
+ *    major; conv [Cout, taps*CinPad] bf16 with K index = tap*CinPad + c, CinPad = roundup(Cin, 64).
+ */
+#ifndef PGT_B200_H_
+#define PGT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum pgt_status {
+  PGT_OK = 0,
+  PGT_ERR_INVALID = -1,      /* bad shape / alignment / null pointer                      */
+  PGT_ERR_CUDA = -2,         /* a CUDA runtime call failed (see pgt_last_cuda_error)       */
+  PGT_ERR_UNSUPPORTED = -3,  /* valid request the sm_100a kernels do not cover            */
+  PGT_ERR_DRIVER = -4        /* cuTensorMapEncodeTiled unavailable / failed               */
+} pgt_status;
+
+enum { PGT_BF16 = 0, PGT_F32 = 1 };
+enum { PGT_ACT_NONE = 0, PGT_ACT_GELU = 1, PGT_ACT_SILU = 2, PGT_ACT_LRELU02 = 3, PGT_ACT_RELU = 4,
+       PGT_ACT_SIGMOID = 5 };
+enum { PGT_EPI_PLAIN = 0,    /* y = act(acc + bias) [+ residual]                           */
+       PGT_EPI_SFT = 1 };    /* y = r + w * (r * aux + (acc + bias)); r = residual         */
+enum { PGT_OUT_NHWC = 0, PGT_OUT_NCHW = 1 };
+
+/* Fused epilogue shared by the tensor-core GEMM / implicit-GEMM conv. */
+typedef struct pgt_epilogue {
+  const float* bias;     /* [N] fp32 or NULL                                               */
+  int32_t act;           /* PGT_ACT_*                                                      */
+  int32_t mode;          /* PGT_EPI_*                                                      */
+  const void* residual;  /* optional [rows, ldr]                                           */
+  int32_t ldr;
+  int32_t res_dtype;     /* PGT_BF16 / PGT_F32                                             */
+  const void* aux;       /* PGT_EPI_SFT: scale tensor, bf16 [rows, ldaux]                  */
+  int32_t ldaux;
+  float sft_w;           /* PGT_EPI_SFT: fusion weight w                                   */
+  void* out;             /* [rows, ldo] (NHWC) or [F, N, H, W] (NCHW, conv only)           */
+  int32_t ldo;
+  int32_t out_dtype;     /* PGT_BF16 / PGT_F32                                             */
+  int32_t out_layout;    /* PGT_OUT_NHWC / PGT_OUT_NCHW                                    */
+  int32_t reserved;
+} pgt_epilogue;
+
+const char* pgt_strerror(int status);
+const char* pgt_last_cuda_error(void);
+int pgt_version(void);
+/* Number of kernel launches issued through this library since the last reset (bench.py's
+ * `gpu_launches` claim). */
+int64_t pgt_launch_count(void);
+void pgt_reset_launch_count(void);
+
+/* ---- tcgen05 GEMM:  out[M,N] = epilogue(A[M,K] * W[N,K]^T)
+ * Replaces nn.Linear / 1x1 Conv2d call sites: WindowAttention3D q/kv/proj
+ * (modules/rstt_layers.py:210-212,231), Mlp fc1/fc2 (:126-131), nn.MultiheadAttention in/out
+ * projections and linear1/linear2 (archs/codeformer_arch.py:105-108,127-136), feat_emb /
+ * idx_pred_layer (archs/pgtformer_arch.py:520-533), quant_conv / post_quant_conv
+ * (archs/tdcrqvae3_arch.py:754-755), convpos, nin_shortcut, SFT 1x1 mixers
+ * (archs/pgtformer_arch.py:454-458).  lda, ldw multiples of 8; A, W 16-byte aligned. */
+int pgt_linear_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+                    const pgt_epilogue* ep, void* stream);
+
+/* ---- tcgen05 implicit-GEMM convolution on NHWC bf16.
+ * ksize in {1,3}; stride in {1,2}; pad_lo = zero rows/cols before the first input row/col
+ * (3x3 s1: 1; Downsample pad(0,1,0,1): 0; ResNet 3x3 s2: 1), the far side is zero-filled as
+ * needed.  Output is [F, Hout, Wout, Cout], Hout = Hin/stride.
+ * Replaces Conv2d 3x3 in TDResnetBlock (modules/rstt_layers.py:875-904), ResBlock / scale / shift
+ * (archs/pgtformer_arch.py:421-432,442-450), Upsample.conv / Downsample.conv
+ * (archs/tdcrqvae3_arch.py:45-52,67-76), conv_in/conv_out, and the BiSeNet convs. */
+int pgt_conv_bf16(const void* x, int F, int Hin, int Win, int Cin, int ldx, const void* Wp, int ldw,
+                  int Cout, int ksize, int stride, int pad_lo, const pgt_epilogue* ep, void* stream);
+
+/* ---- first conv of the encoder: 3x3, Cin=3, fp32 NCHW input -> NHWC bf16 (direct FFMA kernel;
+ * K = 27 is too small for the tensor pipe).  w: fp32 [Cout,3,3,3] (OIHW), bias fp32 [Cout].
+ * Replaces Encoder.conv_in (archs/tdcrqvae3_arch.py:473-477,547). */
+int pgt_conv_in_rgb(const float* x_nchw, int F, int H, int W, const float* w, const float* bias, int Cout,
+                    void* y, int ldy, void* stream);
+
+/* ---- GroupNorm(32, eps) [+ SiLU] on NHWC bf16: y = act((x-mean)*rstd*gamma+beta).
+ * `ws` is a caller-provided fp32 workspace of at least pgt_groupnorm_ws_floats(F, HW, C) floats.
+ * Replaces Normalize()+nonlinearity (modules/rstt_layers.py:754-758,880-881,889-890) and
+ * normalize()+swish (archs/pgtformer_arch.py:406-407,423-428). */
+int64_t pgt_groupnorm_ws_floats(int F, int HW, int C);
+int pgt_groupnorm_silu(const void* x, int ldx, int F, int HW, int C, const float* gamma, const float* beta,
+                       float eps, int apply_silu, void* y, int ldy, float* ws, void* stream);
+
+/* ---- LayerNorm over the last dim (eps 1e-5) of a [T, C] matrix; x may be bf16 or fp32.
+ * y = LN(x) (bf16); if y2 != NULL also y2 = LN(x) + pos (bf16; pos bf16 [T, ldpos]) — the
+ * q = k = LN(x)+pos input of TransformerSALayer (archs/codeformer_arch.py:126-128).
+ * Replaces nn.LayerNorm in VSTSREncoderTransformerBlock (modules/rstt_layers.py:298,335),
+ * TransformerSALayer norm1/norm2, idx_pred_layer.0. */
+int pgt_layernorm(const void* x, int ldx, int x_dtype, int T, int C, const float* gamma, const float* beta,
+                  float eps, void* y, int ldy, const void* pos, int ldpos, void* y2, int ldy2, void* stream);
+
+/* ---- shifted-window spatio-temporal attention core (3 x 4 x 4 windows, N = 48 tokens).
+ * qkv: bf16 [F*H*W, 3C] = [q | k | v] per token in natural (frame, y, x) order; the cyclic
+ * shift, window partition / reverse and the {0,-100} shift mask are index math inside the
+ * kernel; out: bf16 [F*H*W, C] in natural order.  bias_tab: fp32 [heads, 48, 48] (the 245x8
+ * relative-position table expanded through relative_position_index at load time).
+ * Replaces window_partition/roll/WindowAttention3D core/window_reverse
+ * (modules/rstt_layers.py:55-88,213-230,301-329,552-568). */
+int pgt_window_attention(const void* qkv, int ldqkv, int clips, int H, int W, int C, int heads, int shift,
+                         const float* bias_tab, void* out, int ldo, void* stream);
+
+/* ---- global multi-head attention (flash-attention forward, no mask), per clip:
+ * q,k,v: bf16 [clips*L, ld*] with head h at columns [h*d, (h+1)*d); out bf16 [clips*L, ldo].
+ * Replaces the nn.MultiheadAttention core (archs/codeformer_arch.py:105,129-130); the
+ * head-averaged attention weights the reference materialises (need_weights=True) are never
+ * consumed (`[0]` at :130) and are not produced. */
+int pgt_mha_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int clips, int L,
+                int heads, int d, void* out, int ldo, void* stream);
+
+/* ---- codebook ops.
+ * pgt_argmax_gather: idx[t] = argmax_k logits[t,k] (first maximum), quant[t,:] = codebook[idx[t],:].
+ *   logits fp32 [T, K]; codebook fp32 [K(+1), E]; idx int64 [T]; quant bf16/fp32 [T, ldq].
+ *   Replaces logits.argmax(-1) + RQBottleneck.embed_code (archs/pgtformer_arch.py:663-664,
+ *   archs/tdcrqvae3_arch.py:354-368).  If idx_in != NULL the argmax is skipped and idx_in is used
+ *   (teacher-forced codes).
+ * pgt_l2_argmin: idx[t] = argmin_k ||z[t]-e[k]||^2 over the first K codebook rows, lowest index on
+ *   ties; z fp32 [T, E] NHWC; also emits quant = e[idx] when quant != NULL.
+ *   Replaces VQEmbedding.compute_distances + find_nearest_embedding (archs/tdcrqvae3_arch.py:99-126;
+ *   identical copies archs/rqvae_arch.py:218-244, archs/tdrqvae_arch.py:226-251). */
+int pgt_argmax_gather(const float* logits, int T, int K, const float* codebook, int E, const int64_t* idx_in,
+                      int64_t* idx, void* quant, int ldq, int quant_dtype, void* stream);
+int pgt_l2_argmin(const float* z, int T, int E, const float* codebook, int K, int64_t* idx, float* quant,
+                  void* stream);
+
+/* ---- AdaIN: y = (q - mean_q)/std_q * std_l + mean_l per (frame, channel) over HW, unbiased
+ * variance + eps.  q: bf16/fp32 [F, HW, ldq]; l (style) bf16 [F, HW, ldl]; y bf16.
+ * Replaces adaptive_instance_normalization (archs/codeformer_arch.py:15-46). */
+int pgt_adain(const void* q, int ldq, int q_dtype, const void* l, int ldl, int F, int HW, int C, float eps,
+              void* y, int ldy, void* stream);
+
+/* ---- layout / elementwise helpers on NHWC bf16 */
+/* nearest x2 upsample [F,H,W,C] -> [F,2H,2W,C]  (F.interpolate in archs/tdcrqvae3_arch.py:48) */
+int pgt_upsample2x(const void* x, int ldx, int F, int H, int W, int C, void* y, int ldy, void* stream);
+/* strided copy of a [T, C] block (concat building: archs/pgtformer_arch.py:467-475) */
+int pgt_copy2d(const void* x, int ldx, int T, int C, void* y, int ldy, void* stream);
+/* fp32 NCHW -> bf16 NHWC (optionally (x-mean[c])/std[c]); bf16 NHWC -> fp32 NCHW / NHWC */
+int pgt_nchw_f32_to_nhwc_bf16(const float* x, int F, int C, int HW, const float* mean, const float* stdv, void* y,
+                              int ldy, void* stream);
+int pgt_nhwc_bf16_to_f32(const void* x, int ldx, int F, int HW, int C, float* y, int to_nchw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGT_B200_H_ */

@@ -1,0 +1,75 @@
+// Shared host/device helpers for libpgt_b200.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pgt_b200.h"
+
+namespace pgt {
+
+// ---- host-side status plumbing (api.cu)
+void set_cuda_error(cudaError_t e, const char* where);
+void count_launch(int n = 1);
+int num_sms();
+
+#define PGT_CHECK_ARG(cond) \
+  do {                      \
+    if (!(cond)) return PGT_ERR_INVALID; \
+  } while (0)
+
+#define PGT_CUDA_OK(expr)                         \
+  do {                                            \
+    cudaError_t _e = (expr);                      \
+    if (_e != cudaSuccess) {                      \
+      ::pgt::set_cuda_error(_e, #expr);           \
+      return PGT_ERR_CUDA;                        \
+    }                                             \
+  } while (0)
+
+#define PGT_LAUNCH_OK()                           \
+  do {                                            \
+    cudaError_t _e = cudaGetLastError();          \
+    if (_e != cudaSuccess) {                      \
+      ::pgt::set_cuda_error(_e, "kernel launch"); \
+      return PGT_ERR_CUDA;                        \
+    }                                             \
+    ::pgt::count_launch();                        \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- device math
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case PGT_ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+    case PGT_ACT_SILU: return v / (1.0f + __expf(-v));
+    case PGT_ACT_LRELU02: return v > 0.f ? v : 0.2f * v;
+    case PGT_ACT_RELU: return fmaxf(v, 0.f);
+    case PGT_ACT_SIGMOID: return 1.0f / (1.0f + __expf(-v));
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(t);
+}
+__device__ __forceinline__ float bf16_to_f(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace pgt

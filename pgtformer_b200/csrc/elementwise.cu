@@ -1,0 +1,183 @@
+// Layout conversion and small data-movement kernels (HBM-bound, 128-bit vectorised) plus the direct
+// 3-channel first convolution.
+#include "common.cuh"
+
+namespace pgt {
+
+// nearest x2: each thread moves one 16-byte (8 x bf16) vector of an OUTPUT pixel.
+__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int F, int H, int W, int C,
+                                  __nv_bfloat16* __restrict__ y, int ldy) {
+  const int vc = C >> 3;
+  const size_t total = (size_t)F * 4 * H * W * vc;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vc);
+    size_t pix = i / vc;
+    const int ox = (int)(pix % (2 * W)); pix /= (2 * W);
+    const int oy = (int)(pix % (2 * H));
+    const int f = (int)(pix / (2 * H));
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)f * H + (oy >> 1)) * W + (ox >> 1)) * ldx) + v);
+    reinterpret_cast<uint4*>(y + (((size_t)f * 2 * H + oy) * 2 * W + ox) * ldy)[v] = u;
+  }
+}
+
+__global__ void copy2d_kernel(const __nv_bfloat16* __restrict__ x, int ldx, size_t T, int C,
+                              __nv_bfloat16* __restrict__ y, int ldy) {
+  const int vc = C >> 3;
+  const size_t total = T * vc;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t t = i / vc;
+    const int v = (int)(i % vc);
+    reinterpret_cast<uint4*>(y + t * ldy)[v] = __ldg(reinterpret_cast<const uint4*>(x + t * ldx) + v);
+  }
+}
+
+// fp32 NCHW -> bf16 NHWC through a 32x32 shared-memory transpose (coalesced on both sides).
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int C, int HW, const float* __restrict__ mean,
+                                    const float* __restrict__ stdv, __nv_bfloat16* __restrict__ y, int ldy) {
+  __shared__ float tile[32][33];
+  const int f = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, p = p0 + threadIdx.x;
+    float v = 0.f;
+    if (c < C && p < HW) {
+      v = x[((size_t)f * C + c) * HW + p];
+      if (mean != nullptr) v = (v - mean[c]) / stdv[c];
+    }
+    tile[j][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int p = p0 + j, c = c0 + threadIdx.x;
+    if (p < HW && c < ldy && c0 + 32 <= ((C + 31) / 32) * 32) {
+      if (c < C) y[((size_t)f * HW + p) * ldy + c] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+    }
+  }
+}
+
+__global__ void nhwc_to_f32_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int HW, int C, float* __restrict__ y,
+                                   int to_nchw) {
+  __shared__ float tile[32][33];
+  const int f = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int p = p0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (p < HW && c < C) ? __bfloat162float(x[((size_t)f * HW + p) * ldx + c]) : 0.f;
+  }
+  __syncthreads();
+  if (to_nchw) {
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+      const int c = c0 + j, p = p0 + threadIdx.x;
+      if (c < C && p < HW) y[((size_t)f * C + c) * HW + p] = tile[threadIdx.x][j];
+    }
+  } else {
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+      const int p = p0 + j, c = c0 + threadIdx.x;
+      if (c < C && p < HW) y[((size_t)f * HW + p) * C + c] = tile[j][threadIdx.x];
+    }
+  }
+}
+
+// Encoder conv_in: 3x3, 3 -> Cout (<= 64) channels, fp32 math on the fp32 image; one thread = one pixel x 16
+// output channels; weights broadcast from shared memory; 32-byte bf16 stores.
+__global__ void __launch_bounds__(256)
+conv_in_rgb_kernel(const float* __restrict__ x, int H, int W, const float* __restrict__ w, const float* __restrict__ bias,
+                   int Cout, __nv_bfloat16* __restrict__ y, int ldy) {
+  extern __shared__ float sw[];          // [27][Cout] + bias[Cout]
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
+    const int k = i / Cout, co = i % Cout;           // k = ci*9 + dy*3 + dx  (OIHW -> [k][co])
+    sw[i] = w[co * 27 + k];
+  }
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = bias[i];
+  __syncthreads();
+  const int f = blockIdx.z;
+  const int groups = Cout >> 4;
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t pix = gid / groups;
+  const int g = (int)(gid % groups);
+  if (pix >= (size_t)H * W) return;
+  const int py = (int)(pix / W), px = (int)(pix % W);
+  float in[27];
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int yy = py + dy - 1, xx = px + dx - 1;
+        in[ci * 9 + dy * 3 + dx] = (yy >= 0 && yy < H && xx >= 0 && xx < W)
+                                       ? __ldg(x + (((size_t)f * 3 + ci) * H + yy) * W + xx) : 0.f;
+      }
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = sw[27 * Cout + g * 16 + j];
+#pragma unroll
+  for (int k = 0; k < 27; ++k)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = fmaf(in[k], sw[k * Cout + g * 16 + j], acc[j]);
+  uint4 u0, u1;
+  u0.x = pack_bf16x2(acc[0], acc[1]); u0.y = pack_bf16x2(acc[2], acc[3]);
+  u0.z = pack_bf16x2(acc[4], acc[5]); u0.w = pack_bf16x2(acc[6], acc[7]);
+  u1.x = pack_bf16x2(acc[8], acc[9]); u1.y = pack_bf16x2(acc[10], acc[11]);
+  u1.z = pack_bf16x2(acc[12], acc[13]); u1.w = pack_bf16x2(acc[14], acc[15]);
+  uint4* o = reinterpret_cast<uint4*>(y + ((size_t)f * H * W + pix) * ldy + g * 16);
+  o[0] = u0; o[1] = u1;
+}
+
+}  // namespace pgt
+
+using namespace pgt;
+
+static int ew_grid(size_t total, int threads) {
+  size_t b = (total + threads - 1) / threads;
+  const size_t cap = (size_t)num_sms() * 16;
+  return (int)(b < cap ? (b ? b : 1) : cap);
+}
+
+extern "C" int pgt_upsample2x(const void* x, int ldx, int F, int H, int W, int C, void* y, int ldy, void* stream) {
+  PGT_CHECK_ARG(x && y && F > 0 && H > 0 && W > 0 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0);
+  const size_t total = (size_t)F * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, F, H, W, C, reinterpret_cast<__nv_bfloat16*>(y), ldy);
+  PGT_LAUNCH_OK();
+  return PGT_OK;
+}
+
+extern "C" int pgt_copy2d(const void* x, int ldx, int T, int C, void* y, int ldy, void* stream) {
+  PGT_CHECK_ARG(x && y && T > 0 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0);
+  const size_t total = (size_t)T * (C / 8);
+  copy2d_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, (size_t)T, C, reinterpret_cast<__nv_bfloat16*>(y), ldy);
+  PGT_LAUNCH_OK();
+  return PGT_OK;
+}
+
+extern "C" int pgt_nchw_f32_to_nhwc_bf16(const float* x, int F, int C, int HW, const float* mean, const float* stdv,
+                                         void* y, int ldy, void* stream) {
+  PGT_CHECK_ARG(x && y && F > 0 && C > 0 && HW > 0 && ldy >= C && (mean == nullptr) == (stdv == nullptr));
+  dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), F);
+  nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      x, C, HW, mean, stdv, reinterpret_cast<__nv_bfloat16*>(y), ldy);
+  PGT_LAUNCH_OK();
+  return PGT_OK;
+}
+
+extern "C" int pgt_nhwc_bf16_to_f32(const void* x, int ldx, int F, int HW, int C, float* y, int to_nchw, void* stream) {
+  PGT_CHECK_ARG(x && y && F > 0 && C > 0 && HW > 0 && ldx >= C);
+  dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), F);
+  nhwc_to_f32_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C, y, to_nchw);
+  PGT_LAUNCH_OK();
+  return PGT_OK;
+}
+
+extern "C" int pgt_conv_in_rgb(const float* x_nchw, int F, int H, int W, const float* w, const float* bias, int Cout,
+                               void* y, int ldy, void* stream) {
+  PGT_CHECK_ARG(x_nchw && w && bias && y && F > 0 && H > 0 && W > 0 && Cout % 16 == 0 && Cout <= 128 && ldy % 8 == 0);
+  const size_t threads = (size_t)H * W * (Cout / 16);
+  dim3 grid((unsigned)((threads + 255) / 256), 1, F);
+  conv_in_rgb_kernel<<<grid, 256, (27 * Cout + Cout) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      x_nchw, H, W, w, bias, Cout, reinterpret_cast<__nv_bfloat16*>(y), ldy);
+  PGT_LAUNCH_OK();
+  return PGT_OK;
+}

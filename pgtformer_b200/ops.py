@@ -1,0 +1,214 @@
+"""Tensor-level wrappers over the C ABI (ctypes): validate shapes / strides, pass raw device
+pointers and the current CUDA stream.  No computation happens in Python or ATen here.
+
+Activations are channels-last: feature maps are [F, H, W, C] tensors (possibly channel-slice
+views of a wider buffer: stride(-1) == 1, stride(-2) == ld), token matrices are [T, C].
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+from ._lib import (ACT_GELU, ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, BF16, EPI_PLAIN,  # noqa: F401
+                   EPI_SFT, F32, OUT_NCHW, OUT_NHWC, Epilogue)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dt(t):
+    if t.dtype == torch.bfloat16:
+        return BF16
+    if t.dtype == torch.float32:
+        return F32
+    raise TypeError('unsupported dtype %s' % t.dtype)
+
+
+def _rows(t):
+    """Views a channels-last tensor as (rows, C, ld); requires a uniform row stride."""
+    assert t.is_cuda and t.stride(-1) == 1, 'expected a CUDA channels-last tensor'
+    C = t.shape[-1]
+    ld = t.stride(-2) if t.dim() > 1 else C
+    rows = 1
+    exp = ld
+    for d in range(t.dim() - 2, -1, -1):
+        assert t.shape[d] == 1 or t.stride(d) == exp, 'non-uniform row stride'
+        exp *= t.shape[d]
+        rows *= t.shape[d]
+    return rows, C, ld
+
+
+def make_epilogue(out, bias=None, act=ACT_NONE, residual=None, sft_scale=None, sft_w=0.0, nchw=False):
+    ep = Epilogue()
+    ep.bias = bias.data_ptr() if bias is not None else None
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous()
+    ep.act = act
+    ep.mode = EPI_SFT if sft_scale is not None else EPI_PLAIN
+    if residual is not None:
+        _, _, ldr = _rows(residual)
+        ep.residual, ep.ldr, ep.res_dtype = residual.data_ptr(), ldr, _dt(residual)
+    if sft_scale is not None:
+        _, _, lda = _rows(sft_scale)
+        assert sft_scale.dtype == torch.bfloat16
+        ep.aux, ep.ldaux, ep.sft_w = sft_scale.data_ptr(), lda, float(sft_w)
+    ep.out = out.data_ptr()
+    ep.out_dtype = _dt(out)
+    if nchw:
+        assert out.is_contiguous() and out.dtype == torch.float32
+        ep.out_layout, ep.ldo = OUT_NCHW, 0
+    else:
+        ep.out_layout, ep.ldo = OUT_NHWC, _rows(out)[2]
+    return ep
+
+
+def linear(a, w, out, bias=None, act=ACT_NONE, residual=None, K=None, N=None):
+    """out[T,N] = act(a[T,K] @ w[N,K]^T + bias) (+ residual).  a, w bf16; out bf16 / fp32."""
+    lib = L.load()
+    M, Ka, lda = _rows(a)
+    Nw, Kw = w.shape
+    K = K if K is not None else min(Ka, Kw)
+    N = N if N is not None else Nw
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.stride(1) == 1
+    assert _rows(out)[0] == M and out.shape[-1] >= N
+    ep = make_epilogue(out, bias, act, residual)
+    L.check(lib.pgt_linear_bf16(_p(a), lda, _p(w), w.stride(0), M, N, K, ctypes.byref(ep), _stream()))
+    return out
+
+
+def conv(x, wp, cout, out, ksize=3, stride=1, pad_lo=1, bias=None, act=ACT_NONE, residual=None, sft_scale=None,
+         sft_w=0.0, nchw=False):
+    """Implicit-GEMM conv on [F,H,W,Cin] bf16 with packed weights wp [>=cout, k*k*CinPad]."""
+    lib = L.load()
+    F, H, W, Cin = x.shape
+    assert x.dtype == torch.bfloat16 and x.stride(3) == 1 and x.stride(1) == W * x.stride(2) and \
+        (F == 1 or x.stride(0) == H * x.stride(1))
+    ep = make_epilogue(out, bias, act, residual, sft_scale, sft_w, nchw)
+    L.check(lib.pgt_conv_bf16(_p(x), F, H, W, Cin, x.stride(2), _p(wp), wp.stride(0), cout, ksize, stride, pad_lo,
+                              ctypes.byref(ep), _stream()))
+    return out
+
+
+def conv_in_rgb(x_nchw, w, bias, out):
+    lib = L.load()
+    F, C, H, W = x_nchw.shape
+    assert C == 3 and x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
+    assert w.dtype == torch.float32 and w.is_contiguous() and bias.dtype == torch.float32
+    L.check(lib.pgt_conv_in_rgb(_p(x_nchw), F, H, W, _p(w), _p(bias), w.shape[0], _p(out), _rows(out)[2], _stream()))
+    return out
+
+
+_gn_ws = {}
+
+
+def groupnorm_silu(x, gamma, beta, out, eps=1e-6, silu=True):
+    lib = L.load()
+    F = x.shape[0]
+    C = x.shape[-1]
+    HW = x.numel() // (F * C) if x.is_contiguous() else x.shape[1] * x.shape[2]
+    _, _, ldx = _rows(x)
+    _, _, ldy = _rows(out)
+    n = lib.pgt_groupnorm_ws_floats(F, HW, C)
+    key = (x.device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _gn_ws.get(key)
+    if ws is None or ws.numel() < n:
+        ws = torch.empty(max(n, 1 << 16), dtype=torch.float32, device=x.device)
+        _gn_ws[key] = ws
+    L.check(lib.pgt_groupnorm_silu(_p(x), ldx, F, HW, C, _p(gamma), _p(beta), eps, int(silu), _p(out), ldy, _p(ws),
+                                   _stream()))
+    return out
+
+
+def layernorm(x, gamma, beta, out, eps=1e-5, pos=None, out2=None):
+    lib = L.load()
+    T, C, ldx = _rows(x)
+    L.check(lib.pgt_layernorm(_p(x), ldx, _dt(x), T, C, _p(gamma), _p(beta), eps, _p(out), _rows(out)[2],
+                              _p(pos), _rows(pos)[2] if pos is not None else 0,
+                              _p(out2), _rows(out2)[2] if out2 is not None else 0, _stream()))
+    return out
+
+
+def window_attention(qkv, clips, H, W, C, heads, shift, bias_tab, out):
+    lib = L.load()
+    assert qkv.dtype == torch.bfloat16 and bias_tab.dtype == torch.float32 and bias_tab.is_contiguous()
+    L.check(lib.pgt_window_attention(_p(qkv), _rows(qkv)[2], clips, H, W, C, heads, shift, _p(bias_tab), _p(out),
+                                     _rows(out)[2], _stream()))
+    return out
+
+
+def mha(q, k, v, clips, L_, heads, d, out):
+    lib = L.load()
+    L.check(lib.pgt_mha_fwd(_p(q), _rows(q)[2], _p(k), _rows(k)[2], _p(v), _rows(v)[2], clips, L_, heads, d, _p(out),
+                            _rows(out)[2], _stream()))
+    return out
+
+
+def argmax_gather(logits, codebook, idx_out, quant, idx_in=None):
+    lib = L.load()
+    T, K = logits.shape
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and codebook.dtype == torch.float32
+    assert idx_out.dtype == torch.int64
+    L.check(lib.pgt_argmax_gather(_p(logits), T, K, _p(codebook), codebook.shape[1], _p(idx_in), _p(idx_out),
+                                  _p(quant), _rows(quant)[2] if quant is not None else 0,
+                                  _dt(quant) if quant is not None else 0, _stream()))
+    return idx_out, quant
+
+
+def l2_argmin(z, codebook, K, idx_out, quant=None):
+    lib = L.load()
+    T, E = z.shape
+    assert z.dtype == torch.float32 and z.is_contiguous() and codebook.is_contiguous()
+    L.check(lib.pgt_l2_argmin(_p(z), T, E, _p(codebook), K, _p(idx_out), _p(quant), _stream()))
+    return idx_out, quant
+
+
+def adain(q, style, out, eps=1e-5):
+    lib = L.load()
+    F = q.shape[0]
+    C = q.shape[-1]
+    HW = q.shape[1] * q.shape[2] if q.dim() == 4 else q.shape[1]
+    L.check(lib.pgt_adain(_p(q), _rows(q)[2], _dt(q), _p(style), _rows(style)[2], F, HW, C, eps, _p(out),
+                          _rows(out)[2], _stream()))
+    return out
+
+
+def upsample2x(x, out):
+    lib = L.load()
+    F, H, W, C = x.shape
+    L.check(lib.pgt_upsample2x(_p(x), _rows(x)[2], F, H, W, C, _p(out), _rows(out)[2], _stream()))
+    return out
+
+
+def copy2d(x, out):
+    lib = L.load()
+    T, C, ldx = _rows(x)
+    L.check(lib.pgt_copy2d(_p(x), ldx, T, C, _p(out), _rows(out)[2], _stream()))
+    return out
+
+
+def nchw_to_nhwc(x, out, mean=None, std=None):
+    lib = L.load()
+    F, C, H, W = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    L.check(lib.pgt_nchw_f32_to_nhwc_bf16(_p(x), F, C, H * W, _p(mean), _p(std), _p(out), _rows(out)[2], _stream()))
+    return out
+
+
+def nhwc_to_f32(x, out, to_nchw):
+    lib = L.load()
+    F, H, W, C = x.shape
+    L.check(lib.pgt_nhwc_bf16_to_f32(_p(x), _rows(x)[2], F, H * W, C, _p(out), int(to_nchw), _stream()))
+    return out
+
+
+def launch_count():
+    return int(L.load().pgt_launch_count())
+
+
+def reset_launch_count():
+    L.load().pgt_reset_launch_count()

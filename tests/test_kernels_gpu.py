@@ -1,0 +1,347 @@
+"""GPU parity tests, kernel by kernel, THROUGH THE C ABI (pgtformer_b200.ops -> ctypes ->
+libpgt_b200.so) against the CPU oracle (oracle/pgt_oracle.py) on identical bf16-rounded
+inputs.  Tolerances: fp32-output epilogues are compared at 1e-3 * max|ref|;
+bf16 outputs at one bf16 ulp of the oracle value (+ the same absolute floor); index outputs
+bit-exact."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda'
+
+
+def ops():
+    from pgtformer_b200 import ops as o
+    return o
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+def rnd(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g) * scale
+
+
+def check_close(got, ref, what, bf16_out=False, rel=1e-3):
+    got = got.float().cpu()
+    ref = ref.float().cpu()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    assert torch.isfinite(got).all(), what + ': non-finite output'
+    mx = ref.abs().max().item()
+    err = (got - ref).abs()
+    if bf16_out:
+        tol = ref.abs() * 2.0 ** -8 + rel * mx
+        bad = (err > tol)
+        assert not bad.any(), '%s: %d elements beyond 1 bf16 ulp (max err %.3e, max|ref| %.3e)' % (
+            what, int(bad.sum()), err.max().item(), mx)
+    else:
+        assert err.max().item() <= rel * mx, '%s: max err %.3e > %.1e * max|ref| %.3e' % (what, err.max().item(), rel, mx)
+
+
+def pack_conv_weight(w):
+    """OIHW fp32 -> [Cout, k*k*CinPad] bf16, K index = tap*CinPad + c (see include/pgt_b200.h)."""
+    co, ci, kh, kw = w.shape
+    cp = (ci + 63) // 64 * 64
+    wp = torch.zeros(co, kh * kw, cp)
+    wp[:, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, kh * kw, ci)
+    return bf(wp.reshape(co, kh * kw * cp)).contiguous()
+
+
+# ------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize('M,N,K,act,res,out_dt', [
+    (300, 96, 192, 'gelu', True, torch.float32),
+    (1024, 768, 256, None, False, torch.bfloat16),
+    (130, 1024, 512, None, False, torch.float32),
+    (4096, 256, 256, None, True, torch.bfloat16),
+    (257, 32, 512, 'silu', False, torch.float32),
+    (20000, 512, 1024, None, False, torch.float32),
+    (192, 1536, 512, None, False, torch.bfloat16),
+])
+def test_linear(M, N, K, act, res, out_dt):
+    o = ops()
+    a, w, b = bf(rnd((M, K), 1)), bf(rnd((N, K), 2, K ** -0.5)), rnd((N,), 3, 0.1)
+    r = bf(rnd((M, N), 4)) if res else None
+    ref = a.float() @ w.float().t() + b
+    if act == 'gelu':
+        ref = F.gelu(ref)
+    elif act == 'silu':
+        ref = F.silu(ref)
+    if res:
+        ref = ref + r.float()
+    out = torch.empty(M, N, dtype=out_dt, device=DEV)
+    actc = {None: o.ACT_NONE, 'gelu': o.ACT_GELU, 'silu': o.ACT_SILU}[act]
+    o.linear(a.to(DEV), w.to(DEV), out, bias=b.to(DEV), act=actc, residual=r.to(DEV) if res else None)
+    torch.cuda.synchronize()
+    check_close(out, ref, 'linear', bf16_out=(out_dt == torch.bfloat16))
+
+
+def test_linear_k_tail_and_strided_views():
+    """K = 57 (convpos) inside a 64-wide buffer; output into a channel slice of a wider buffer."""
+    o = ops()
+    M, N, K = 200, 512, 57
+    a_full = torch.zeros(M, 64)
+    a_full[:, :K] = rnd((M, K), 5)
+    w_full = torch.zeros(N, 64)
+    w_full[:, :K] = rnd((N, K), 6, 0.1)
+    a, w = bf(a_full).to(DEV), bf(w_full).to(DEV)
+    buf = torch.zeros(M, 1056, dtype=torch.bfloat16, device=DEV)
+    o.linear(a, w, buf[:, 512:1024], K=K)
+    torch.cuda.synchronize()
+    ref = bf(a_full).float() @ bf(w_full).float().t()
+    check_close(buf[:, 512:1024], ref, 'linear k-tail', bf16_out=True)
+    assert buf[:, :512].abs().max() == 0 and buf[:, 1024:].abs().max() == 0
+
+
+# ------------------------------------------------------------------------------------ conv
+def conv_ref(x_nhwc, w, b, stride=1, pad=(1, 1, 1, 1)):
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    return F.conv2d(F.pad(x, pad), w, b, stride=stride).permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize('Fr,H,W,Cin,Cout', [
+    (3, 16, 16, 64, 64),
+    (3, 8, 8, 512, 512),       # two frames per 128-row tile, odd frame count
+    (6, 32, 32, 256, 128),
+    (3, 8, 128, 128, 64),      # one image row per tile
+    (3, 16, 16, 288, 128),     # Cin = 4.5 x 64: channel tail zero-filled by TMA
+    (2, 64, 64, 64, 96),
+    (3, 4, 4, 64, 64),
+])
+def test_conv3x3(Fr, H, W, Cin, Cout):
+    o = ops()
+    x = bf(rnd((Fr, H, W, Cin), 10))
+    w = bf(rnd((Cout, Cin, 3, 3), 11, (9 * Cin) ** -0.5)).float()
+    b = rnd((Cout,), 12, 0.1)
+    out = torch.empty(Fr, H, W, Cout, dtype=torch.float32, device=DEV)
+    o.conv(x.to(DEV), pack_conv_weight(w).to(DEV), Cout, out, bias=b.to(DEV))
+    torch.cuda.synchronize()
+    check_close(out, conv_ref(x, w, b), 'conv3x3')
+
+
+def test_conv3x3_epilogues_and_nchw():
+    o = ops()
+    Fr, H, W, C = 3, 16, 16, 128
+    x = bf(rnd((Fr, H, W, C), 20))
+    w = bf(rnd((C, C, 3, 3), 21, (9 * C) ** -0.5)).float()
+    b = rnd((C,), 22, 0.1)
+    res, scale = bf(rnd((Fr, H, W, C), 23)), bf(rnd((Fr, H, W, C), 24))
+    wp = pack_conv_weight(w).to(DEV)
+    y = conv_ref(x, w, b)
+    out = torch.empty(Fr, H, W, C, dtype=torch.bfloat16, device=DEV)
+    o.conv(x.to(DEV), wp, C, out, bias=b.to(DEV), act=o.ACT_LRELU02)
+    check_close(out, F.leaky_relu(y, 0.2), 'conv+lrelu', bf16_out=True)
+    o.conv(x.to(DEV), wp, C, out, bias=b.to(DEV), residual=res.to(DEV))
+    check_close(out, y + res.float(), 'conv+residual', bf16_out=True)
+    o.conv(x.to(DEV), wp, C, out, bias=b.to(DEV), residual=res.to(DEV), sft_scale=scale.to(DEV), sft_w=0.7)
+    check_close(out, res.float() + 0.7 * (res.float() * scale.float() + y), 'conv+sft', bf16_out=True)
+    # Cout = 3, fp32 NCHW output (decoder.conv_out)
+    w3 = bf(rnd((3, C, 3, 3), 25, (9 * C) ** -0.5)).float()
+    b3 = rnd((3,), 26, 0.1)
+    out3 = torch.empty(Fr, 3, H, W, dtype=torch.float32, device=DEV)
+    o.conv(x.to(DEV), pack_conv_weight(w3).to(DEV), 3, out3, bias=b3.to(DEV), nchw=True)
+    check_close(out3, conv_ref(x, w3, b3).permute(0, 3, 1, 2), 'conv nchw')
+
+
+@pytest.mark.parametrize('Fr,H,W,C,pad_lo', [(3, 16, 16, 64, 0), (3, 32, 32, 128, 0), (3, 16, 16, 64, 1), (6, 8, 8, 256, 1)])
+def test_conv3x3_stride2(Fr, H, W, C, pad_lo):
+    """pad_lo=0: Downsample pad(0,1,0,1) (tdcrqvae3_arch.py:67-76); pad_lo=1: ResNet 3x3 s2 p1."""
+    o = ops()
+    x = bf(rnd((Fr, H, W, C), 30))
+    w = bf(rnd((C, C, 3, 3), 31, (9 * C) ** -0.5)).float()
+    b = rnd((C,), 32, 0.1)
+    out = torch.empty(Fr, H // 2, W // 2, C, dtype=torch.float32, device=DEV)
+    o.conv(x.to(DEV), pack_conv_weight(w).to(DEV), C, out, stride=2, pad_lo=pad_lo, bias=b.to(DEV))
+    torch.cuda.synchronize()
+    pad = (0, 1, 0, 1) if pad_lo == 0 else (1, 1, 1, 1)
+    check_close(out, conv_ref(x, w, b, stride=2, pad=pad), 'conv s2')
+
+
+def test_conv1x1_stride2():
+    o = ops()
+    Fr, H, W, Cin, Cout = 3, 16, 16, 64, 128
+    x = bf(rnd((Fr, H, W, Cin), 33))
+    w = bf(rnd((Cout, Cin, 1, 1), 34, Cin ** -0.5)).float()
+    out = torch.empty(Fr, H // 2, W // 2, Cout, dtype=torch.float32, device=DEV)
+    o.conv(x.to(DEV), pack_conv_weight(w).to(DEV), Cout, out, ksize=1, stride=2, pad_lo=0)
+    check_close(out, conv_ref(x, w, None, stride=2, pad=(0, 0, 0, 0)), 'conv1x1 s2')
+
+
+def test_conv_in_rgb():
+    o = ops()
+    x = torch.rand(3, 3, 32, 32, generator=torch.Generator().manual_seed(40))
+    w, b = rnd((64, 3, 3, 3), 41, 27 ** -0.5), rnd((64,), 42, 0.1)
+    out = torch.empty(3, 32, 32, 64, dtype=torch.bfloat16, device=DEV)
+    o.conv_in_rgb(x.to(DEV), w.to(DEV), b.to(DEV), out)
+    check_close(out, F.conv2d(x, w, b, padding=1).permute(0, 2, 3, 1), 'conv_in', bf16_out=True)
+
+
+# ------------------------------------------------------------------------------------ norms
+@pytest.mark.parametrize('Fr,HW,C', [(3, 64, 64), (3, 1024, 512), (2, 4096, 128), (3, 256, 1056), (3, 1024, 288), (3, 64, 544)])
+def test_groupnorm_silu(Fr, HW, C):
+    o = ops()
+    x = bf(rnd((Fr, HW, C), 50) * 2 + 0.3)
+    gam, bet = 1 + 0.1 * rnd((C,), 51), 0.1 * rnd((C,), 52)
+    out = torch.empty(Fr, HW, C, dtype=torch.bfloat16, device=DEV)
+    o.groupnorm_silu(x.to(DEV), gam.to(DEV), bet.to(DEV), out)
+    ref = F.silu(F.group_norm(x.float().permute(0, 2, 1), 32, gam, bet, eps=1e-6)).permute(0, 2, 1)
+    check_close(out, ref, 'groupnorm+silu', bf16_out=True)
+    o.groupnorm_silu(x.to(DEV), gam.to(DEV), bet.to(DEV), out, silu=False)
+    check_close(out, F.group_norm(x.float().permute(0, 2, 1), 32, gam, bet, eps=1e-6).permute(0, 2, 1), 'groupnorm', bf16_out=True)
+
+
+@pytest.mark.parametrize('T,C,dt', [(1000, 256, torch.bfloat16), (3072, 512, torch.bfloat16), (77, 512, torch.float32)])
+def test_layernorm(T, C, dt):
+    o = ops()
+    x = (rnd((T, C), 60) * 1.5 + 0.2).to(dt)
+    gam, bet = 1 + 0.1 * rnd((C,), 61), 0.1 * rnd((C,), 62)
+    pos = bf(rnd((T, C), 63))
+    y = torch.empty(T, C, dtype=torch.bfloat16, device=DEV)
+    y2 = torch.empty_like(y)
+    o.layernorm(x.to(DEV), gam.to(DEV), bet.to(DEV), y, pos=pos.to(DEV), out2=y2)
+    ref = F.layer_norm(x.float(), (C,), gam, bet, 1e-5)
+    check_close(y, ref, 'layernorm', bf16_out=True)
+    check_close(y2, ref + pos.float(), 'layernorm+pos', bf16_out=True)
+
+
+def test_adain():
+    from oracle import pgt_oracle as O
+    o = ops()
+    Fr, HW, C = 3, 64, 512
+    q, l = rnd((Fr, HW, C), 70), bf(rnd((Fr, HW, C), 71) * 0.5 + 0.1)
+    out = torch.empty(Fr, HW, C, dtype=torch.bfloat16, device=DEV)
+    o.adain(q.to(DEV), l.to(DEV), out)
+    ref = O.adain(q.permute(0, 2, 1).reshape(Fr, C, 8, 8), l.float().permute(0, 2, 1).reshape(Fr, C, 8, 8))
+    check_close(out, ref.reshape(Fr, C, HW).permute(0, 2, 1), 'adain', bf16_out=True)
+
+
+# ------------------------------------------------------------------------------------ codebook
+def test_argmax_gather_bit_exact(synth_sd):
+    from oracle import pgt_oracle as O
+    o = ops()
+    cb = synth_sd['quantizer.codebooks.0.weight']
+    T, K = 3 * 64 + 5, 1024
+    logits = rnd((T, K), 80)
+    logits[0, 17] = logits[0].max() + 1
+    logits[0, 900] = logits[0, 17]              # duplicate maximum -> first index wins
+    logits[1, :] = 0.25                         # all ties -> index 0
+    idx = torch.empty(T, dtype=torch.int64, device=DEV)
+    quant = torch.empty(T, 512, dtype=torch.float32, device=DEV)
+    o.argmax_gather(logits.to(DEV), cb.to(DEV), idx, quant)
+    ref_idx = logits.argmax(-1)
+    assert torch.equal(idx.cpu(), ref_idx)
+    assert idx[0] == 17 and idx[1] == 0
+    assert torch.equal(quant.cpu(), O.embed_code(cb, ref_idx.view(T, 1)))
+    qb = torch.empty(T, 512, dtype=torch.bfloat16, device=DEV)
+    forced = torch.randint(0, 1024, (T,), generator=torch.Generator().manual_seed(81))
+    o.argmax_gather(logits.to(DEV), cb.to(DEV), idx, qb, idx_in=forced.to(DEV))
+    assert torch.equal(idx.cpu(), forced) and torch.equal(qb.cpu(), bf(cb[forced]))
+
+
+@pytest.mark.parametrize('regime', ['random', 'near_code', 'duplicates'])
+def test_l2_argmin_bit_exact(synth_sd, regime):
+    from oracle import pgt_oracle as O
+    o = ops()
+    cb = synth_sd['quantizer.codebooks.0.weight'].clone()
+    T = 3 * 8 * 8 * 4 + 7
+    if regime == 'random':
+        z = rnd((T, 512), 90)
+    elif regime == 'near_code':
+        pick = torch.randint(0, 1024, (T,), generator=torch.Generator().manual_seed(91))
+        z = cb[pick] + 0.05 * rnd((T, 512), 92)
+    else:
+        cb[700] = cb[3]
+        cb[701] = cb[3]
+        z = cb[3].expand(T, 512) + 0.01 * rnd((T, 512), 93)
+    idx = torch.empty(T, dtype=torch.int64, device=DEV)
+    quant = torch.empty(T, 512, dtype=torch.float32, device=DEV)
+    o.l2_argmin(z.to(DEV).contiguous(), cb.to(DEV).contiguous(), 1024, idx, quant)
+    ref, _ = O.l2_argmin_exact(cb, z)
+    assert torch.equal(idx.cpu(), ref), 'mismatches: %d' % int((idx.cpu() != ref).sum())
+    assert torch.equal(quant.cpu(), cb[ref])
+    assert int(idx.max()) < 1024
+    if regime == 'duplicates':
+        assert (idx.cpu() == 3).all()
+    # the reference's own fp32 addmm formula agrees wherever its margin is meaningful
+    ref32 = O.l2_argmin(cb, z)
+    assert (ref32 == ref).float().mean() > 0.995
+
+
+# ------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize('C,H,W,clips', [(256, 16, 16, 1), (512, 8, 8, 2), (256, 32, 32, 1), (512, 4, 4, 1)])
+@pytest.mark.parametrize('shifted', [False, True])
+def test_window_attention_core(C, H, W, clips, shifted):
+    """Core only (q/kv/proj identity): compares against the oracle's roll/partition/attention/reverse."""
+    from oracle import pgt_oracle as O
+    from pgtformer_b200.weights import relative_position_index
+    o = ops()
+    heads, d = 8, C // 8
+    T = clips * 3 * H * W
+    qkv = bf(rnd((T, 3 * C), 100, 1.0))
+    table = 0.5 * rnd((245, heads), 101)
+    idx = relative_position_index()
+    bias_tab = table[idx.view(-1)].view(48, 48, heads).permute(2, 0, 1).contiguous()
+    out = torch.empty(T, C, dtype=torch.bfloat16, device=DEV)
+    o.window_attention(qkv.to(DEV), clips, H, W, C, heads, 2 if shifted else 0, bias_tab.to(DEV), out)
+    torch.cuda.synchronize()
+    # oracle: feed q, k, v through identity projections
+    x = qkv.float().view(clips, 3, H, W, 3 * C)
+    do_shift = shifted and H > 4 and W > 4
+    xs = torch.roll(x, (-2, -2), (2, 3)) if do_shift else x
+    xw = O.window_partition(xs).view(-1, 48, 3 * C)
+    q = xw[..., :C].view(-1, 48, heads, d).permute(0, 2, 1, 3) * d ** -0.5
+    k = xw[..., C:2 * C].view(-1, 48, heads, d).permute(0, 2, 1, 3)
+    v = xw[..., 2 * C:].view(-1, 48, heads, d).permute(0, 2, 1, 3)
+    attn = q @ k.transpose(-2, -1) + bias_tab[None]
+    if do_shift:
+        mask = O.shift_mask(H, W)
+        nW = mask.shape[0]
+        attn = (attn.view(-1, nW, heads, 48, 48) + mask[None, :, None]).view(-1, heads, 48, 48)
+    ow = (attn.softmax(-1) @ v).transpose(1, 2).reshape(-1, 48, C)
+    ref = O.window_reverse(ow.view(-1, 3, 4, 4, C), clips, 3, H, W)
+    if do_shift:
+        ref = torch.roll(ref, (2, 2), (2, 3))
+    check_close(out, ref.reshape(T, C), 'window attention', bf16_out=True, rel=4e-3)
+
+
+@pytest.mark.parametrize('L,clips', [(192, 2), (3072, 1), (48, 1), (200, 1)])
+def test_mha_fwd(L, clips):
+    o = ops()
+    heads, d, E = 8, 64, 512
+    q, k, v = bf(rnd((clips * L, E), 110)), bf(rnd((clips * L, E), 111)), bf(rnd((clips * L, E), 112))
+    out = torch.empty(clips * L, E, dtype=torch.bfloat16, device=DEV)
+    o.mha(q.to(DEV), k.to(DEV), v.to(DEV), clips, L, heads, d, out)
+    torch.cuda.synchronize()
+    sh = lambda a: a.float().view(clips, L, heads, d).permute(0, 2, 1, 3)
+    ref = (torch.softmax(sh(q) @ sh(k).transpose(-1, -2) / math.sqrt(d), -1) @ sh(v)).permute(0, 2, 1, 3).reshape(clips * L, E)
+    check_close(out, ref, 'mha', bf16_out=True, rel=4e-3)
+
+
+# ------------------------------------------------------------------------------------ layout
+def test_layout_kernels():
+    o = ops()
+    x = torch.rand(3, 3, 16, 16, generator=torch.Generator().manual_seed(120))
+    mean, std = torch.tensor([0.485, 0.456, 0.406]), torch.tensor([0.229, 0.224, 0.225])
+    y = torch.zeros(3, 16, 16, 8, dtype=torch.bfloat16, device=DEV)
+    o.nchw_to_nhwc(x.to(DEV), y, mean.to(DEV), std.to(DEV))
+    ref = ((x - mean.view(1, 3, 1, 1)) / std.view(1, 3, 1, 1)).permute(0, 2, 3, 1)
+    check_close(y[..., :3], ref, 'nchw->nhwc', bf16_out=True)
+    assert y[..., 3:].abs().max() == 0
+    a = bf(rnd((2, 8, 8, 64), 121))
+    up = torch.empty(2, 16, 16, 64, dtype=torch.bfloat16, device=DEV)
+    o.upsample2x(a.to(DEV), up)
+    assert torch.equal(up.cpu(), F.interpolate(a.float().permute(0, 3, 1, 2), scale_factor=2.0, mode='nearest').permute(0, 2, 3, 1).to(torch.bfloat16))
+    buf = torch.zeros(2, 8, 8, 160, dtype=torch.bfloat16, device=DEV)
+    o.copy2d(a.to(DEV), buf[..., 64:128])
+    assert torch.equal(buf[..., 64:128].cpu(), a) and buf[..., :64].abs().max() == 0
+    f32 = torch.empty(2, 64, 8, 8, dtype=torch.float32, device=DEV)
+    o.nhwc_to_f32(a.to(DEV), f32, True)
+    assert torch.equal(f32.cpu(), a.float().permute(0, 3, 1, 2))
+    f32b = torch.empty(2, 8, 8, 64, dtype=torch.float32, device=DEV)
+    o.nhwc_to_f32(a.to(DEV), f32b, False)
+    assert torch.equal(f32b.cpu(), a.float())
