@@ -151,6 +151,9 @@ int pgt_adain(const void* q, int ldq, int q_dtype, const void* l, int ldl, int F
 int pgt_upsample2x(const void* x, int ldx, int F, int H, int W, int C, void* y, int ldy, void* stream);
 /* strided copy of a [T, C] block (concat building: archs/pgtformer_arch.py:467-475) */
 int pgt_copy2d(const void* x, int ldx, int T, int C, void* y, int ldy, void* stream);
+/* temporal regroup for the SFT block's cross-frame 1x1 mixers (archs/pgtformer_arch.py:467-472):
+ * dir 0: x [clips,3,P,C] -> y [clips,P,3C] (channel = frame*C + c); dir 1: the inverse. */
+int pgt_regroup_frames(const void* x, int ldx, int clips, int P, int C, void* y, int ldy, int dir, void* stream);
 /* fp32 NCHW -> bf16 NHWC (optionally (x-mean[c])/std[c]); bf16 NHWC -> fp32 NCHW / NHWC */
 int pgt_nchw_f32_to_nhwc_bf16(const float* x, int F, int C, int HW, const float* mean, const float* stdv, void* y,
                               int ldy, void* stream);

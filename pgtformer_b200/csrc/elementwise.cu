@@ -181,3 +181,36 @@ extern "C" int pgt_conv_in_rgb(const float* x_nchw, int F, int H, int W, const f
   PGT_LAUNCH_OK();
   return PGT_OK;
 }
+
+// ---- temporal regroup used by the SFT fusion block's cross-frame 1x1 mixers
+// dir 0: x [b,3,P,C] -> y [b,P,3*C] (channel = frame*C + c);   dir 1: the inverse.
+namespace pgt {
+__global__ void regroup_frames_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int b, int P, int C,
+                                      __nv_bfloat16* __restrict__ y, int ldy, int dir) {
+  const int vc = C >> 3;
+  const size_t total = (size_t)b * 3 * P * vc;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vc);
+    size_t r = i / vc;
+    const int p = (int)(r % P); r /= P;
+    const int fr = (int)(r % 3);
+    const int clip = (int)(r / 3);
+    const size_t frame_row = ((size_t)clip * 3 + fr) * P + p;          // [b,3,P] row
+    const size_t clip_row = (size_t)clip * P + p;                      // [b,P] row
+    if (dir == 0)
+      reinterpret_cast<uint4*>(y + clip_row * ldy + fr * C)[v] = __ldg(reinterpret_cast<const uint4*>(x + frame_row * ldx) + v);
+    else
+      reinterpret_cast<uint4*>(y + frame_row * ldy)[v] = __ldg(reinterpret_cast<const uint4*>(x + clip_row * ldx + fr * C) + v);
+  }
+}
+}  // namespace pgt
+
+extern "C" int pgt_regroup_frames(const void* x, int ldx, int clips, int P, int C, void* y, int ldy, int dir,
+                                  void* stream) {
+  PGT_CHECK_ARG(x && y && clips > 0 && P > 0 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && (dir == 0 || dir == 1));
+  const size_t total = (size_t)clips * 3 * P * (C / 8);
+  regroup_frames_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, clips, P, C, reinterpret_cast<__nv_bfloat16*>(y), ldy, dir);
+  PGT_LAUNCH_OK();
+  return PGT_OK;
+}

@@ -1,0 +1,335 @@
+"""B200 forward engine for PGTFormer: one-time weight repack into kernel layouts + the launch
+sequence of `PGTFormer.forward` / `TDCRQVAE3.forward` over libpgt_b200.so.
+
+Data layout in HBM: every activation is channels-last bf16 — feature maps
+[F=clips*3, H, W, C], token matrices [T, C] — except the tensors the reference returns
+(`out` fp32 NCHW, `logits` fp32, `lq_feat` fp32 NHWC) and the residual stream of the 9-layer global
+transformer (fp32, it decides the code indices).  Frames of a clip are contiguous, so the
+frame-major token order of the global transformer (`archs/pgtformer_arch.py:614,640`) is the
+natural row order and no permute is ever materialised.
+
+Every op is a call into the C ABI; there is no PyTorch/CPU fallback — without the CUDA library
+construction fails.  The one exception, stated in DESIGN.md, is the BiSeNet parsing net (2.1 %
+of the FLOPs), which runs through cuDNN in round 1.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .spec import Arch
+
+BF = torch.bfloat16
+
+
+def _pack_conv(w):
+    """OIHW fp32 -> [Cout, k*k*CinPad] bf16 (K index = tap*CinPad + c)."""
+    co, ci, kh, kw = w.shape
+    cp = (ci + 63) // 64 * 64
+    wp = torch.zeros(co, kh * kw, cp, dtype=torch.float32, device=w.device)
+    wp[:, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, kh * kw, ci)
+    return wp.reshape(co, kh * kw * cp).to(BF).contiguous()
+
+
+def _pack_lin(w):
+    """[N, K] (or [N, K, 1, 1]) fp32 -> [N, roundup(K, 8)] bf16."""
+    w = w.reshape(w.shape[0], -1)
+    n, k = w.shape
+    kp = (k + 7) // 8 * 8
+    if kp != k:
+        w = F.pad(w, (0, kp - k))
+    return w.to(BF).contiguous()
+
+
+class Engine:
+    def __init__(self, network_g, state_dict, device):
+        ops.L.load()                                   # fail loudly if the CUDA library is missing
+        self.arch = Arch(network_g)
+        self.dev = torch.device(device)
+        if self.dev.type != 'cuda':
+            raise RuntimeError('pgtformer_b200 has no CPU path: the engine needs a CUDA (sm_100a) device')
+        self.w = {}
+        self._sd = {k: v.detach().to(self.dev) for k, v in state_dict.items()}
+        self._repack()
+
+    # ------------------------------------------------------------------ weight repack (load time)
+    def _f32(self, name):
+        return self._sd[name].float().contiguous()
+
+    def _repack(self):
+        sd, w = self._sd, self.w
+        for name, t in sd.items():
+            if name.startswith('conditionnet.'):
+                continue
+            if name.endswith('.weight') and t.dim() == 4:
+                if name == 'encoder.conv_in.weight':
+                    w[name] = t.float().contiguous()
+                elif t.shape[2] == 3:
+                    w[name] = _pack_conv(t.float())
+                else:
+                    w[name] = _pack_lin(t.float())
+            elif name.endswith('.weight') and t.dim() == 2 and 'codebooks' not in name:
+                w[name] = _pack_lin(t.float())
+            elif t.dtype.is_floating_point and t.dim() == 1:
+                w[name] = t.float().contiguous()
+        w['codebook'] = self._f32('quantizer.codebooks.0.weight')
+        # Swin blocks: fused [q | k | v] projection and the expanded relative-position bias
+        for name in list(sd):
+            if name.endswith('.attn.relative_position_bias_table'):
+                p = name[:-len('.relative_position_bias_table')]
+                heads = sd[name].shape[1]
+                idx = sd[p + '.relative_position_index'].view(-1).long()
+                w[p + '.bias_tab'] = sd[name].float()[idx].view(48, 48, heads).permute(2, 0, 1).contiguous()
+                w[p + '.qkv.weight'] = _pack_lin(torch.cat([sd[p + '.q.weight'], sd[p + '.kv.weight']], 0).float())
+                w[p + '.qkv.bias'] = torch.cat([sd[p + '.q.bias'], sd[p + '.kv.bias']], 0).float().contiguous()
+        # global transformer: in_proj split into the (q,k) projection of LN(x)+pos and the v projection of LN(x)
+        E = self.arch.dim_embd
+        for i in range(self.arch.n_layers):
+            p = 'ft_layers.%d.self_attn' % i
+            wi, bi = sd[p + '.in_proj_weight'].float(), sd[p + '.in_proj_bias'].float()
+            w[p + '.qk.weight'], w[p + '.qk.bias'] = _pack_lin(wi[:2 * E]), bi[:2 * E].contiguous()
+            w[p + '.v.weight'], w[p + '.v.bias'] = _pack_lin(wi[2 * E:]), bi[2 * E:].contiguous()
+        self.img_mean = torch.tensor([0.485, 0.456, 0.406], device=self.dev).view(1, 3, 1, 1)
+        self.img_std = torch.tensor([0.229, 0.224, 0.225], device=self.dev).view(1, 3, 1, 1)
+        self._cond = {k[len('conditionnet.'):]: v.float() for k, v in sd.items() if k.startswith('conditionnet.')}
+
+    # ------------------------------------------------------------------ small helpers
+    def _new(self, *shape, dtype=BF):
+        return torch.empty(*shape, dtype=dtype, device=self.dev)
+
+    def _gn(self, x, p, silu=True):
+        return ops.groupnorm_silu(x, self.w[p + '.weight'], self.w[p + '.bias'], self._new(*x.shape), silu=silu)
+
+    def _conv3(self, x, p, cout, out=None, **kw):
+        Fr, H, W, _ = x.shape
+        stride = kw.get('stride', 1)
+        if out is None:
+            out = self._new(Fr, H // stride, W // stride, cout)
+        return ops.conv(x, self.w[p + '.weight'], cout, out, bias=self.w.get(p + '.bias'), **kw)
+
+    def _lin(self, x, p, n, out=None, out_dtype=BF, **kw):
+        if out is None:
+            out = self._new(*x.shape[:-1], n, dtype=out_dtype)
+        return ops.linear(x, self.w[p + '.weight'], out, bias=self.w.get(p + '.bias'), N=n, **kw)
+
+    # ------------------------------------------------------------------ blocks
+    def td_resblock(self, x, p, cout):
+        """TDResnetBlock (`modules/rstt_layers.py:875-904`): 2 x (GN+SiLU -> conv3x3), residual in the
+        second conv's epilogue (1x1 nin_shortcut first when the width changes)."""
+        h = self._conv3(self._gn(x, p + '.norm1'), p + '.conv1', cout)
+        sc = self._lin(x, p + '.nin_shortcut', cout) if (p + '.nin_shortcut.weight') in self.w else x
+        return self._conv3(self._gn(h, p + '.norm2'), p + '.conv2', cout, residual=sc)
+
+    def swin_block(self, x, p, heads, shift):
+        """VSTSREncoderTransformerBlock (`modules/rstt_layers.py:284-338`) on [F,H,W,C]."""
+        Fr, H, W, C = x.shape
+        w = self.w
+        y = ops.layernorm(x, w[p + '.norm1.weight'], w[p + '.norm1.bias'], self._new(Fr, H, W, C))
+        qkv = self._lin(y, p + '.attn.qkv', 3 * C)
+        a = ops.window_attention(qkv, Fr // 3, H, W, C, heads, shift, w[p + '.attn.bias_tab'], self._new(Fr, H, W, C))
+        x = self._lin(a, p + '.attn.proj', C, residual=x)
+        y = ops.layernorm(x, w[p + '.norm2.weight'], w[p + '.norm2.bias'], self._new(Fr, H, W, C))
+        m = self._lin(y, p + '.mlp.fc1', C, act=ops.ACT_GELU)
+        return self._lin(m, p + '.mlp.fc2', C, residual=x)
+
+    def encoder_layer(self, x, p, heads, depth):
+        for i in range(depth):
+            x = self.swin_block(x, '%s.blocks.%d' % (p, i), heads, 2 if i % 2 == 1 else 0)
+        return x
+
+    def fuse_sft(self, enc, dec, key, wgt):
+        """Fuse_sft_block (`archs/pgtformer_arch.py:460-484`); the final
+        dec + w*(dec*scale + shift) is the epilogue of the last `shift` conv."""
+        p = 'fuse_convs_dict.' + key
+        Fr, H, W, C = dec.shape
+        b, P = Fr // 3, H * W
+        cat = self._new(Fr, H, W, 2 * C + 32)
+        ops.copy2d(enc, cat[..., :C])
+        ops.copy2d(dec, cat[..., C:2 * C])
+        tcat = self._new(b, P, 192)
+        ops.regroup_frames(self._lin(enc, p + '.tconvenc', 32), tcat[..., :96], b, P, 32, 0)
+        ops.regroup_frames(self._lin(dec, p + '.tconvdec', 32), tcat[..., 96:], b, P, 32, 0)
+        fut = ops.regroup_frames(self._lin(tcat, p + '.tfusion0', 96), self._new(Fr, P, 32), b, P, 32, 1)
+        self._lin(fut, p + '.tfusion1', 32, out=cat.view(Fr, P, 2 * C + 32)[..., 2 * C:])
+        e = p + '.encode_enc'
+        h = self._conv3(self._gn(cat, e + '.norm1'), e + '.conv1', C)
+        sc = self._lin(cat, e + '.conv_out', C)
+        ef = self._conv3(self._gn(h, e + '.norm2'), e + '.conv2', C, residual=sc)
+        scale = self._conv3(self._conv3(ef, p + '.scale.0', C, act=ops.ACT_LRELU02), p + '.scale.2', C)
+        sh = self._conv3(ef, p + '.shift.0', C, act=ops.ACT_LRELU02)
+        return self._conv3(sh, p + '.shift.2', C, residual=dec, sft_scale=scale, sft_w=wgt)
+
+    # ------------------------------------------------------------------ parsing net (cuDNN, round 1)
+    def _bisenet(self, x):
+        sd = self._cond
+        conv = lambda p, t, s=1, pad=0: F.conv2d(t, sd[p + '.weight'], None, s, pad)
+        bn = lambda p, t: F.batch_norm(t, sd[p + '.running_mean'], sd[p + '.running_var'], sd[p + '.weight'], sd[p + '.bias'], False, 0.0, 1e-5)
+        cbr = lambda p, t, s=1, pad=1: F.relu(bn(p + '.bn', conv(p + '.conv', t, s, pad)))
+
+        def block(p, t, s):
+            r = F.relu(bn(p + '.bn1', conv(p + '.conv1', t, s, 1)))
+            r = bn(p + '.bn2', conv(p + '.conv2', r, 1, 1))
+            if (p + '.downsample.0.weight') in sd:
+                t = bn(p + '.downsample.1', conv(p + '.downsample.0', t, s))
+            return F.relu(t + r)
+
+        def arm(p, t):
+            f = cbr(p + '.conv', t)
+            a = torch.sigmoid(bn(p + '.bn_atten', conv(p + '.conv_atten', f.mean((2, 3), keepdim=True))))
+            return f * a
+
+        H, W = x.shape[2:]
+        t = F.max_pool2d(F.relu(bn('cp.resnet.bn1', conv('cp.resnet.conv1', x, 2, 3))), 3, 2, 1)
+        feats = []
+        for li, s in ((1, 1), (2, 2), (3, 2), (4, 2)):
+            t = block('cp.resnet.layer%d.0' % li, t, s)
+            t = block('cp.resnet.layer%d.1' % li, t, 1)
+            feats.append(t)
+        f8, f16, f32 = feats[1], feats[2], feats[3]
+        avg = cbr('cp.conv_avg', f32.mean((2, 3), keepdim=True), 1, 0)
+        u32 = cbr('cp.conv_head32', F.interpolate(arm('cp.arm32', f32) + avg, f16.shape[2:], mode='nearest'))
+        u16 = cbr('cp.conv_head16', F.interpolate(arm('cp.arm16', f16) + u32, f8.shape[2:], mode='nearest'))
+        fc = cbr('ffm.convblk', torch.cat([f8, u16], 1), 1, 0)
+        at = torch.sigmoid(conv('ffm.conv2', F.relu(conv('ffm.conv1', fc.mean((2, 3), keepdim=True)))))
+        fuse = fc * at + fc
+        o0 = conv('conv_out.conv_out', cbr('conv_out.conv', fuse))
+        o1 = conv('conv_out16.conv_out', cbr('conv_out16.conv', u16))
+        o2 = conv('conv_out32.conv_out', cbr('conv_out32.conv', u32))
+        size = (H // 16, W // 16)
+        o0 = F.interpolate(o0, size, mode='bilinear', align_corners=True)
+        o1 = F.interpolate(o1, size, mode='bilinear', align_corners=True)
+        return torch.cat([o0, o1, o2], 1)
+
+    # ------------------------------------------------------------------ encoder / decoder
+    def encoder(self, x):
+        """Encoder.forward (`archs/tdcrqvae3_arch.py:540-573`); x fp32 NCHW -> (h [F,h,w,z], feats)."""
+        a = self.arch
+        Fr, _, H, W = x.shape
+        h = ops.conv_in_rgb(x, self.w['encoder.conv_in.weight'], self.w['encoder.conv_in.bias'], self._new(Fr, H, W, a.ch))
+        feats = []
+        for lvl in range(a.num_levels):
+            for blk in range(a.num_res_blocks):
+                h = self.td_resblock(h, 'encoder.down.%d.block.%d' % (lvl, blk), a.level_ch[lvl])
+                if a.level_has_attn[lvl]:
+                    h = self.encoder_layer(h, 'encoder.down.%d.attn.%d' % (lvl, blk), a.num_heads[lvl], a.depths[lvl])
+            feats.append(h)
+            if lvl != a.num_levels - 1:
+                h = self._conv3(h, 'encoder.down.%d.downsample.conv' % lvl, a.level_ch[lvl], stride=2, pad_lo=0)
+        h = self.td_resblock(h, 'encoder.mid.block_1', a.level_ch[-1])
+        h = self.encoder_layer(h, 'encoder.mid.attn_1', a.num_heads[-1], a.depths[-1])
+        h = self.td_resblock(h, 'encoder.mid.block_2', a.level_ch[-1])
+        zc = 2 * a.z_channels if a.double_z else a.z_channels
+        return self._conv3(self._gn(h, 'encoder.norm_out'), 'encoder.conv_out', zc), feats
+
+    def decoder(self, z, feats=None, wgt=0.0):
+        """Decoder.forward (`archs/tdcrqvae3_arch.py:672-707`) / the inlined variant with SFT fusion
+        (`archs/pgtformer_arch.py:680-710`).  z: [F,h,w,z_channels] bf16 -> out fp32 NCHW."""
+        a = self.arch
+        h = self._conv3(z, 'decoder.conv_in', a.level_ch[-1])
+        h = self.td_resblock(h, 'decoder.mid.block_1', a.level_ch[-1])
+        h = self.encoder_layer(h, 'decoder.mid.attn_1', a.num_heads[-1], a.depths[-1])
+        h = self.td_resblock(h, 'decoder.mid.block_2', a.level_ch[-1])
+        for lvl in reversed(range(a.num_levels)):
+            for blk in range(a.num_res_blocks + 1):
+                h = self.td_resblock(h, 'decoder.up.%d.block.%d' % (lvl, blk), a.level_ch[lvl])
+                if a.level_has_attn[lvl]:
+                    h = self.encoder_layer(h, 'decoder.up.%d.attn.%d' % (lvl, blk), a.num_heads[lvl], a.depths[lvl])
+            if feats is not None and lvl in a.fuse_level_key and wgt > 0:
+                h = self.fuse_sft(feats[lvl], h, a.fuse_level_key[lvl], wgt)
+            if lvl != 0:
+                Fr, H, W, C = h.shape
+                up = ops.upsample2x(h, self._new(Fr, 2 * H, 2 * W, C))
+                h = self._conv3(up, 'decoder.up.%d.upsample.conv' % lvl, C)
+        Fr, H, W, _ = h.shape
+        out = self._new(Fr, a.out_ch, H, W, dtype=torch.float32)
+        self._conv3(self._gn(h, 'decoder.norm_out'), 'decoder.conv_out', a.out_ch, out=out, nchw=True)
+        return out
+
+    def parse_pos(self, x):
+        """BiSeNet parsing features -> convpos 1x1 -> positional term [T, 512] bf16
+        (`archs/pgtformer_arch.py:606-614`)."""
+        Fr, _, H, W = x.shape
+        hh, ww = H // 16, W // 16
+        cond = self._bisenet((x - self.img_mean) / self.img_std)
+        cond_nhwc = torch.zeros(Fr, hh, ww, 64, dtype=BF, device=self.dev)
+        ops.nchw_to_nhwc(cond.contiguous(), cond_nhwc)
+        return self._lin(cond_nhwc.view(Fr * hh * ww, 64), 'convpos', 512, K=57)
+
+    def global_transformer(self, lq, pos, clips):
+        """feat_emb + 9 x TransformerSALayer + idx_pred_layer (`archs/pgtformer_arch.py:638-649`,
+        `archs/codeformer_arch.py:121-137`) on [T, E] rows in natural (clip, frame, y, x) order;
+        fp32 residual stream; returns fp32 logits [T, n_embed]."""
+        a, wd = self.arch, self.w
+        T, E = lq.shape[0], a.dim_embd
+        L = T // clips
+        q = self._lin(lq, 'feat_emb', E, out_dtype=torch.float32)
+        for i in range(a.n_layers):
+            p = 'ft_layers.%d' % i
+            y, y2 = self._new(T, E), self._new(T, E)
+            ops.layernorm(q, wd[p + '.norm1.weight'], wd[p + '.norm1.bias'], y, pos=pos, out2=y2)
+            qk = self._lin(y2, p + '.self_attn.qk', 2 * E)
+            v = self._lin(y, p + '.self_attn.v', E)
+            att = ops.mha(qk[:, :E], qk[:, E:], v, clips, L, a.n_head, E // a.n_head, self._new(T, E))
+            q = self._lin(att, p + '.self_attn.out_proj', E, out_dtype=torch.float32, residual=q)
+            y = ops.layernorm(q, wd[p + '.norm2.weight'], wd[p + '.norm2.bias'], self._new(T, E))
+            m = self._lin(y, p + '.linear1', 2 * E, act=ops.ACT_GELU)
+            q = self._lin(m, p + '.linear2', E, out_dtype=torch.float32, residual=q)
+        y = ops.layernorm(q, wd['idx_pred_layer.0.weight'], wd['idx_pred_layer.0.bias'], self._new(T, E))
+        return self._lin(y, 'idx_pred_layer.1', a.n_embed, out_dtype=torch.float32)
+
+    # ------------------------------------------------------------------ full forwards
+    @torch.no_grad()
+    def forward(self, x, w=1.0, adain=True, code_only=False, force_codes=None):
+        """PGTFormer.forward (`archs/pgtformer_arch.py:598-714`).  x: fp32 [b*3,3,H,W] in [0,1] on the
+        device.  Returns (out, logits [b*3,h,w,1,K], lq_feat [b*3,h,w,E]) like the reference."""
+        a = self.arch
+        x = x.to(self.dev, torch.float32).contiguous()
+        Fr, _, H, W = x.shape
+        if Fr % a.tf != 0 or H % 64 != 0 or W % 64 != 0:
+            raise ValueError('expected b*3 frames with H, W multiples of 64, got %s' % (tuple(x.shape),))
+        hh, ww = H // 16, W // 16
+        T, E = Fr * hh * ww, a.dim_embd
+        wd = self.w
+        pos = self.parse_pos(x)
+        # encoder
+        h, feats = self.encoder(x)
+        h = h.view(T, -1)
+        lq32 = self._lin(h, 'quant_conv', a.embed_dim, out_dtype=torch.float32)
+        lq = self._lin(h, 'quant_conv', a.embed_dim)
+        logits = self.global_transformer(lq, pos, Fr // 3)
+        logits5 = logits.view(Fr, hh, ww, 1, a.n_embed)
+        lq_nhwc = lq32.view(Fr, hh, ww, a.embed_dim)
+        if code_only:
+            return logits5, lq_nhwc
+        # quantise: argmax + codebook gather, AdaIN against lq, post_quant_conv
+        codes = torch.empty(T, dtype=torch.int64, device=self.dev)
+        quant = self._new(T, a.embed_dim, dtype=torch.float32)
+        idx_in = force_codes.to(self.dev).reshape(T).contiguous() if force_codes is not None else None
+        ops.argmax_gather(logits, wd['codebook'], codes, quant, idx_in=idx_in)
+        self.last_codes = codes.view(Fr, hh, ww, 1)
+        if adain:
+            quant = ops.adain(quant.view(Fr, hh * ww, -1), lq.view(Fr, hh * ww, -1), self._new(Fr, hh * ww, a.embed_dim))
+        else:
+            quant = quant.to(BF)
+        z = self._lin(quant.reshape(T, a.embed_dim), 'post_quant_conv', a.z_channels)
+        out = self.decoder(z.view(Fr, hh, ww, a.z_channels), feats, float(w))
+        return out, logits5, lq_nhwc
+
+    @torch.no_grad()
+    def forward_vq(self, x, code_only=False):
+        """TDCRQVAE3.forward (`archs/tdcrqvae3_arch.py:760-783`): encode -> L2 argmin -> embed -> decode."""
+        a = self.arch
+        x = x.to(self.dev, torch.float32).contiguous()
+        Fr, _, H, W = x.shape
+        hh, ww = H // 16, W // 16
+        T = Fr * hh * ww
+        h, _ = self.encoder(x)
+        z_e = self._lin(h.view(T, -1), 'quant_conv', a.embed_dim, out_dtype=torch.float32)
+        codes = torch.empty(T, dtype=torch.int64, device=self.dev)
+        z_q = self._new(T, a.embed_dim, dtype=torch.float32)
+        ops.l2_argmin(z_e, self.w['codebook'], a.n_embed, codes, z_q)
+        loss = (z_e - z_q).pow(2).mean()
+        codes = codes.view(Fr, hh, ww, 1)
+        if code_only:
+            return z_q.view(Fr, hh, ww, -1), loss, codes
+        z = self._lin(z_q.to(BF), 'post_quant_conv', a.z_channels)
+        return self.decoder(z.view(Fr, hh, ww, a.z_channels)), loss, codes

@@ -191,6 +191,12 @@ def copy2d(x, out):
     return out
 
 
+def regroup_frames(x, out, clips, P, C, direction):
+    lib = L.load()
+    L.check(lib.pgt_regroup_frames(_p(x), _rows(x)[2], clips, P, C, _p(out), _rows(out)[2], direction, _stream()))
+    return out
+
+
 def nchw_to_nhwc(x, out, mean=None, std=None):
     lib = L.load()
     F, C, H, W = x.shape
