@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""bench.py — clips/s of the PGTFormer forward path (BASELINE.json metric) on N B200s.
+
+A "step" is one `PGTFormer.forward` over `--clips` synthetic 3-frame 512x512 clips per GPU
+(default 16 = BASELINE configs[2] at N=1, configs[3] at N=8: weak scaling, clips are independent).
+  value       whole-job clips/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e         the same metric through the drop-in `PGTFormer.__call__` with HOST (pinned) inputs:
+              H2D copy of the clips and D2H copy of `out` inside the timed region
+  roofline    dominant kernel (tcgen05 implicit-GEMM conv / GEMM): algorithmic FLOPs / live per-launch
+              device time (CUDA events on the launching stream, separate profiled pass of the same steps)
+  cpu_baseline  the CPU oracle (port of the reference's PyTorch path) on the host cores, N=1 rank 0 only
+`--impl reference` times that CPU path alone (the reference has no CUDA code of its own and cannot
+travel to the GPU box; `oracle/pgt_oracle.py` is pinned to it by tests/golden/).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOPS_PER_CLIP = {128: 236.8e9, 256: None, 512: 3952.0e9, 1024: 17895.0e9}     # SURVEY 8(d), 2*MAC
+
+
+def flops_per_clip(H):
+    s = H / 512.0
+    return (3952.0e9 - 173.9e9) * s * s + 173.9e9 * s ** 4
+
+
+def load_network_g():
+    import yaml
+    with open(os.path.join(ROOT, 'options', 'release_test_stage_IIII_dont_need_align_version.yml')) as f:
+        return yaml.safe_load(f)['network_g']
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, 'measured'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, col in (('hw_slowdown', 5), ('hw_thermal_slowdown', 6), ('sw_thermal_slowdown', 7),
+                                  ('sw_power_cap', 8)):
+                    if r[col].lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def cpu_oracle_clips_per_s(H, warmup, steps):
+    """Times the CPU oracle (port of the reference forward) one clip per step; returns (clips/s, cores)."""
+    import torch
+    from oracle import pgt_oracle as O
+    from pgtformer_b200.spec import build_spec
+    from pgtformer_b200.weights import synth_state_dict
+    torch.set_num_threads(os.cpu_count())
+    arch, spec = build_spec(load_network_g())
+    sd = synth_state_dict(spec, 0)
+    x = torch.rand(3, 3, H, H, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.pgtformer_forward(sd, arch, x, 1.0, True)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.pgtformer_forward(sd, arch, x, 1.0, True)
+        dt = time.perf_counter() - t0
+    return steps / dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path (oracle port), host cores only."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    warm = min(args.warmup, 1)
+    val, cores = cpu_oracle_clips_per_s(args.size, warm, args.steps)
+    sample = '%d steps x 1 clip (3x%dx%d), %d warm-up, fp32 PyTorch CPU' % (args.steps, args.size, args.size, warm)
+    line = {'impl': 'reference', 'metric': 'clips_per_s', 'value': val, 'unit': 'clips/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': warm, 'ms_per_step': 1000.0 / val, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'PGTFormer.forward, 1 clip/step of 3x%dx%d on host CPU' % (args.size, args.size),
+                       'size': args.size, 'clips_per_step': 1},
+            'cpu_baseline': {'value': val, 'unit': 'clips/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': 'clips/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--clips', type=int, default=16, help='clips per GPU per step')
+    ap.add_argument('--size', type=int, default=512)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from archs.pgtformer_arch import PGTFormer
+    from pgtformer_b200 import ops
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    warmup = max(args.warmup, 3)
+
+    opt = load_network_g()
+    kw = dict(opt)
+    kw.pop('type')
+    model = PGTFormer(**kw).to(dev)
+    model.eval()
+    b, H = args.clips, args.size
+    g = torch.Generator().manual_seed(1 + rank)
+    x_host = torch.rand(b * 3, 3, H, H, generator=g).pin_memory()
+    x_dev = x_host.to(dev)
+    out_host = torch.empty(b * 3, 3, H, H, dtype=torch.float32).pin_memory()
+    gathered = torch.empty(world * b * 3, 3, H, H, dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step_resident():
+        out = model(x_dev, w=1, adain=True)[0]
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)      # the path's one collective
+        return out
+
+    def step_e2e():
+        xd = x_host.to(dev, non_blocking=True)
+        out = model(xd, w=1, adain=True)[0]
+        out_host.copy_(out, non_blocking=True)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.reset_launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = ops.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * b * args.steps / (ms / 1000.0)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_val = world * b * args.steps / (ms_e2e / 1000.0)
+
+    # roofline of the dominant kernel: separate profiled pass (events around every launch of the class)
+    torch.cuda.synchronize()
+    ops.profile_begin()
+    for _ in range(args.steps):
+        model(x_dev, w=1, adain=True)
+    prof = ops.profile_end()
+    peaks, peak_kind = measured_peaks()
+
+    if rank == 0:
+        work, pms, n = prof['gemm_tc']
+        achieved = work / (pms / 1000.0) / 1e12 if pms > 0 else 0.0
+        peak = float(peaks.get('bf16_tflops_sustained', 1400.0))
+        total_ms = sum(v[1] for v in prof.values())
+        breakdown = {k: {'ms_per_step': v[1] / args.steps, 'launches_per_step': v[2] / args.steps,
+                         'work_per_step': v[0] / args.steps} for k, v in prof.items() if v[2] > 0}
+        line = {
+            'metric': 'clips_per_s', 'value': value, 'unit': 'clips/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': 'PGTFormer.forward on %d clips/GPU of 3x%dx%d (BASELINE configs[%s]), w=1, adain, '
+                                   'random-init pgtformer-base' % (b, H, H, '2' if world == 1 else '3'),
+                       'clips_per_gpu': b, 'size': H, 'global_clips': world * b, 'parallelism': 'dp%d' % world,
+                       'l2_policy': 'inputs and activations (GBs per step) exceed the 126 MB L2; no flush needed',
+                       'flops_per_clip': flops_per_clip(H)},
+            'e2e': {'value': e2e_val, 'unit': 'clips/s', 'ms_per_step': ms_e2e / args.steps,
+                    'h2d_bytes_per_step': x_host.numel() * 4, 'd2h_bytes_per_step': out_host.numel() * 4},
+            'gpu_launches': launches,
+            'clocks': clocks,
+            'roofline': {'bound': 'tensor', 'kernel': 'gemm_tc_kernel (tcgen05 implicit-GEMM conv / GEMM)',
+                         'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+                         'peak_kind': peak_kind + ' bf16_tflops_sustained', 'traffic': None,
+                         'launches_per_step': n / args.steps, 'kernel_ms_per_step': pms / args.steps,
+                         'share_of_profiled_kernel_time': pms / total_ms if total_ms > 0 else None,
+                         'pass': 'separate profiled pass of the same %d steps' % args.steps,
+                         'end_to_end_frac': value / world * flops_per_clip(H) / (peak * 1e12)},
+            'kernel_breakdown': breakdown,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                v, cores = cpu_oracle_clips_per_s(H, 1, 1)
+                line['cpu_baseline'] = {'value': v, 'unit': 'clips/s', 'cores': cores, 'kind': 'port',
+                                        'sample': '1 clip (3x%dx%d) timed once after 1 warm-up, fp32 PyTorch CPU oracle' % (H, H)}
+            except Exception as e:                     # never lose the GPU line to a CPU-side problem
+                line['cpu_baseline'] = {'value': None, 'unit': 'clips/s', 'cores': os.cpu_count(), 'kind': 'port',
+                                        'sample': 'failed: %r' % (e,)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

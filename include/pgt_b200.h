@@ -65,6 +65,15 @@ int pgt_version(void);
 int64_t pgt_launch_count(void);
 void pgt_reset_launch_count(void);
 
+/* Optional per-launch profiler (bench.py's roofline figures): between begin and end every launch of
+ * the classes below is bracketed by CUDA events on its own stream; end() synchronises and returns,
+ * per class, the summed algorithmic work (FLOPs, or bytes for the HBM-bound classes), the summed
+ * device time in ms and the launch count.  Arrays have PGT_PROF_CLASSES entries. */
+enum { PGT_PROF_GEMM = 0, PGT_PROF_WINDOW_ATTN = 1, PGT_PROF_MHA = 2, PGT_PROF_ARGMAX = 3, PGT_PROF_ARGMIN = 4,
+       PGT_PROF_NORM = 5, PGT_PROF_MOVE = 6, PGT_PROF_CLASSES = 8 };
+int pgt_profile_begin(void);
+int pgt_profile_end(double* work, double* ms, int64_t* launches);
+
 /* ---- tcgen05 GEMM:  out[M,N] = epilogue(A[M,K] * W[N,K]^T)
  * Replaces nn.Linear / 1x1 Conv2d call sites: WindowAttention3D q/kv/proj
  * (modules/rstt_layers.py:210-212,231), Mlp fc1/fc2 (:126-131), nn.MultiheadAttention in/out

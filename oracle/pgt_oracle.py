@@ -201,9 +201,9 @@ def fuse_sft(sd, p, enc, dec, w):
     """Fuse_sft_block.forward (`archs/pgtformer_arch.py:460-484`); enc, dec are [b*3,C,h,w]."""
     BD, C, h, wf = enc.shape
     b, d = BD // FRAMES, FRAMES
-    enct = conv(sd, p + '.tconvenc', enc).view(b, d * 32, h, wf)
-    dect = conv(sd, p + '.tconvdec', dec).view(b, d * 32, h, wf)
-    fut = conv(sd, p + '.tfusion0', torch.cat([enct, dect], 1)).view(b * d, 32, h, wf)
+    enct = conv(sd, p + '.tconvenc', enc).contiguous().view(b, d * 32, h, wf)
+    dect = conv(sd, p + '.tconvdec', dec).contiguous().view(b, d * 32, h, wf)
+    fut = conv(sd, p + '.tfusion0', torch.cat([enct, dect], 1)).contiguous().view(b * d, 32, h, wf)
     fut = conv(sd, p + '.tfusion1', fut)
     e = sft_resblock(sd, p + '.encode_enc', torch.cat([enc, dec, fut], 1))
     scale = conv(sd, p + '.scale.2', F.leaky_relu(conv(sd, p + '.scale.0', e, padding=1), 0.2), padding=1)

@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 
@@ -23,7 +24,40 @@ int num_sms() {
   }
   return n;
 }
+
+// ---- optional per-launch profiler: CUDA events on the launching stream around every launch of a class
+struct ProfRec { cudaEvent_t e0, e1; int cls; double work; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+bool prof_enabled() { return g_prof_on; }
+void prof_before(int cls, double work, cudaStream_t st) {
+  ProfRec r; r.cls = cls; r.work = work;
+  cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, st);
+  g_prof.push_back(r);
+}
+void prof_after(cudaStream_t st) { cudaEventRecord(g_prof.back().e1, st); }
 }  // namespace pgt
+
+extern "C" int pgt_profile_begin(void) {
+  pgt::g_prof.clear();
+  pgt::g_prof_on = true;
+  return PGT_OK;
+}
+extern "C" int pgt_profile_end(double* work, double* ms, int64_t* launches) {
+  pgt::g_prof_on = false;
+  for (int i = 0; i < PGT_PROF_CLASSES; ++i) { work[i] = 0; ms[i] = 0; launches[i] = 0; }
+  for (auto& r : pgt::g_prof) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess &&
+        r.cls >= 0 && r.cls < PGT_PROF_CLASSES) {
+      work[r.cls] += r.work; ms[r.cls] += t; launches[r.cls] += 1;
+    }
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  pgt::g_prof.clear();
+  return PGT_OK;
+}
 
 extern "C" const char* pgt_strerror(int status) {
   switch (status) {

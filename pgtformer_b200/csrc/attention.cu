@@ -295,6 +295,7 @@ extern "C" int pgt_window_attention(const void* qkv, int ldqkv, int clips, int H
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid((H / 4) * (W / 4), clips);
   const size_t smem = (size_t)8 * 2 * WIN_N * (d + 8) * 2;
+  ProfScope ps(PGT_PROF_WINDOW_ATTN, 4.0 * WIN_N * WIN_N * C * (double)grid.x * grid.y, st);
   if (d == 32) {
     static bool attr32 = false;
     if (!attr32) {
@@ -325,6 +326,7 @@ extern "C" int pgt_mha_fwd(const void* q, int ldq, const void* k, int ldk, const
   if (d != 64) return PGT_ERR_UNSUPPORTED;
   dim3 grid(ceil_div(L, FA_BM), heads, clips);
   const size_t smem = (size_t)4 * FA_BN * (64 + 8) * 2;
+  ProfScope ps(PGT_PROF_MHA, 4.0 * (double)L * L * d * heads * clips, static_cast<cudaStream_t>(stream));
   mha_fwd_kernel<64><<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(q), ldq, reinterpret_cast<const __nv_bfloat16*>(k), ldk,
       reinterpret_cast<const __nv_bfloat16*>(v), ldv, L, heads, reinterpret_cast<__nv_bfloat16*>(out), ldo);

@@ -210,6 +210,8 @@ extern "C" int pgt_argmax_gather(const float* logits, int T, int K, const float*
   PGT_CHECK_ARG(quant == nullptr || (codebook != nullptr && E % 4 == 0 && ldq % 4 == 0));
   PGT_CHECK_ARG((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
   const int warps = 8;
+  ProfScope ps(PGT_PROF_ARGMAX, (double)T * K * 4 + (double)T * 8 + (quant ? (double)T * E * (quant_dtype == PGT_BF16 ? 2 : 4) : 0.0),
+               static_cast<cudaStream_t>(stream));
   argmax_gather_kernel<<<ceil_div(T, warps), warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       logits, T, K, codebook, E, idx_in, idx, quant, ldq, quant_dtype);
   PGT_LAUNCH_OK();
@@ -220,6 +222,7 @@ extern "C" int pgt_l2_argmin(const float* z, int T, int E, const float* codebook
                              void* stream) {
   PGT_CHECK_ARG(z && codebook && idx && T > 0 && K > 0 && E > 0 && E % AM_KC == 0);
   PGT_CHECK_ARG((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(codebook) & 15) == 0);
+  ProfScope ps(PGT_PROF_ARGMIN, 2.0 * T * (double)K * E, static_cast<cudaStream_t>(stream));
   l2_argmin_kernel<<<ceil_div(T, AM_TT), 256, 0, static_cast<cudaStream_t>(stream)>>>(z, T, E, codebook, K, idx, quant);
   PGT_LAUNCH_OK();
   return PGT_OK;

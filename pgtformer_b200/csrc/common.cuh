@@ -12,6 +12,14 @@ namespace pgt {
 void set_cuda_error(cudaError_t e, const char* where);
 void count_launch(int n = 1);
 int num_sms();
+bool prof_enabled();
+void prof_before(int cls, double work, cudaStream_t st);
+void prof_after(cudaStream_t st);
+struct ProfScope {      // RAII: events around one launch when the profiler is on
+  cudaStream_t st; bool on;
+  ProfScope(int cls, double work, cudaStream_t s) : st(s), on(prof_enabled()) { if (on) prof_before(cls, work, s); }
+  ~ProfScope() { if (on) prof_after(st); }
+};
 
 #define PGT_CHECK_ARG(cond) \
   do {                      \

@@ -47,6 +47,7 @@ struct GemmParams {
   float sft_w;
   void* out;
   int ldo, out_dtype, out_layout;
+  double flops;      // algorithmic 2*M*N*K with the un-padded K (host-side accounting only)
 };
 
 template <int BN>
@@ -370,7 +371,10 @@ static int launch_gemm(const CUtensorMap& tmA, const void* W, int ldw, GemmParam
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  {
+    ProfScope ps(PGT_PROF_GEMM, p.flops, stream);
+    gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  }
   PGT_LAUNCH_OK();
   return PGT_OK;
 }
@@ -429,6 +433,7 @@ extern "C" int pgt_linear_bf16(const void* A, int lda, const void* W, int ldw, i
   p.M = M; p.N = N; p.K = K;
   p.num_kb = ceil_div(K, BK);
   p.m_tiles = ceil_div(M, BM);
+  p.flops = 2.0 * M * (double)N * K;
   int rc = fill_epilogue(p, ep);
   if (rc != PGT_OK) return rc;
   CUtensorMap tmA;
@@ -479,6 +484,7 @@ extern "C" int pgt_conv_bf16(const void* x, int F, int Hin, int Win, int Cin, in
   p.tiles_y = ceil_div(p.H, th);
   p.m_tiles = p.tiles_x * p.tiles_y * ceil_div(F, tn);
   p.M = F * p.H * p.W;
+  p.flops = 2.0 * p.M * (double)Cout * (ksize * ksize * Cin);
   if (p.mode == MODE_CONV_S1) {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)F};
     uint64_t str[3] = {(uint64_t)ldx * 2, (uint64_t)Win * ldx * 2, (uint64_t)Hin * Win * ldx * 2};

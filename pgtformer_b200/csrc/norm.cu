@@ -266,6 +266,7 @@ extern "C" int pgt_groupnorm_silu(const void* x, int ldx, int F, int HW, int C, 
   PGT_CHECK_ARG(x && y && ws && gamma && beta && F > 0 && HW > 0);
   PGT_CHECK_ARG(C % 32 == 0 && C % 8 == 0 && C / 8 <= GN_THREADS && ldx % 8 == 0 && ldy % 8 == 0);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope ps(PGT_PROF_NORM, 3.0 * F * (double)HW * C * 2, st);     // read, read, write (bf16)
   const int nchunks = gn_chunks(HW);
   const int ppc = ceil_div(HW, nchunks);
   gn_stats_kernel<<<dim3(nchunks, F), GN_THREADS, 2 * C * sizeof(float), st>>>(

@@ -218,3 +218,18 @@ def launch_count():
 
 def reset_launch_count():
     L.load().pgt_reset_launch_count()
+
+
+PROF_CLASSES = ('gemm_tc', 'window_attn', 'mha', 'argmax_gather', 'l2_argmin', 'groupnorm', 'move', 'other')
+
+
+def profile_begin():
+    L.check(L.load().pgt_profile_begin())
+
+
+def profile_end():
+    """-> {class: (work, ms, launches)}; work is FLOPs (gemm/attention/argmin) or bytes (argmax/norm)."""
+    n = len(PROF_CLASSES)
+    work, ms, cnt = (ctypes.c_double * n)(), (ctypes.c_double * n)(), (ctypes.c_int64 * n)()
+    L.check(L.load().pgt_profile_end(work, ms, cnt))
+    return {PROF_CLASSES[i]: (work[i], ms[i], int(cnt[i])) for i in range(n)}
