@@ -73,6 +73,8 @@ enum { PGT_PROF_GEMM = 0, PGT_PROF_WINDOW_ATTN = 1, PGT_PROF_MHA = 2, PGT_PROF_A
        PGT_PROF_NORM = 5, PGT_PROF_MOVE = 6, PGT_PROF_CLASSES = 8 };
 int pgt_profile_begin(void);
 int pgt_profile_end(double* work, double* ms, int64_t* launches);
+/* same, and also writes one CSV row per launch (class, description, work, ms) to `path` (host string). */
+int pgt_profile_end_csv(const char* path, double* work, double* ms, int64_t* launches);
 
 /* ---- tcgen05 GEMM:  out[M,N] = epilogue(A[M,K] * W[N,K]^T)
  * Replaces nn.Linear / 1x1 Conv2d call sites: WindowAttention3D q/kv/proj

@@ -32,6 +32,7 @@ SIGNATURES = {
     'pgt_reset_launch_count': (None, []),
     'pgt_profile_begin': (c_int, []),
     'pgt_profile_end': (c_int, [c_void_p, c_void_p, c_void_p]),
+    'pgt_profile_end_csv': (c_int, [c_char_p, c_void_p, c_void_p, c_void_p]),
     'pgt_linear_bf16': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, POINTER(Epilogue), c_void_p]),
     'pgt_conv_bf16': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
                               c_int, POINTER(Epilogue), c_void_p]),

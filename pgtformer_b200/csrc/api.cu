@@ -26,12 +26,13 @@ int num_sms() {
 }
 
 // ---- optional per-launch profiler: CUDA events on the launching stream around every launch of a class
-struct ProfRec { cudaEvent_t e0, e1; int cls; double work; };
+struct ProfRec { cudaEvent_t e0, e1; int cls; double work; char desc[96]; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 bool prof_enabled() { return g_prof_on; }
-void prof_before(int cls, double work, cudaStream_t st) {
+void prof_before(int cls, double work, cudaStream_t st, const char* desc) {
   ProfRec r; r.cls = cls; r.work = work;
+  snprintf(r.desc, sizeof(r.desc), "%s", desc ? desc : "");
   cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
   cudaEventRecord(r.e0, st);
   g_prof.push_back(r);
@@ -44,6 +45,15 @@ extern "C" int pgt_profile_begin(void) {
   pgt::g_prof_on = true;
   return PGT_OK;
 }
+extern "C" int pgt_profile_end(double* work, double* ms, int64_t* launches);
+static FILE* g_prof_csv = nullptr;
+extern "C" int pgt_profile_end_csv(const char* path, double* work, double* ms, int64_t* launches) {
+  g_prof_csv = fopen(path, "w");
+  if (g_prof_csv) fprintf(g_prof_csv, "class,desc,work,ms\n");
+  int rc = pgt_profile_end(work, ms, launches);
+  if (g_prof_csv) { fclose(g_prof_csv); g_prof_csv = nullptr; }
+  return rc;
+}
 extern "C" int pgt_profile_end(double* work, double* ms, int64_t* launches) {
   pgt::g_prof_on = false;
   for (int i = 0; i < PGT_PROF_CLASSES; ++i) { work[i] = 0; ms[i] = 0; launches[i] = 0; }
@@ -52,6 +62,7 @@ extern "C" int pgt_profile_end(double* work, double* ms, int64_t* launches) {
     if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess &&
         r.cls >= 0 && r.cls < PGT_PROF_CLASSES) {
       work[r.cls] += r.work; ms[r.cls] += t; launches[r.cls] += 1;
+      if (g_prof_csv) fprintf(g_prof_csv, "%d,%s,%.6e,%.6f\n", r.cls, r.desc, r.work, t);
     }
     cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
   }

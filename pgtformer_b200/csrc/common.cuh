@@ -13,11 +13,11 @@ void set_cuda_error(cudaError_t e, const char* where);
 void count_launch(int n = 1);
 int num_sms();
 bool prof_enabled();
-void prof_before(int cls, double work, cudaStream_t st);
+void prof_before(int cls, double work, cudaStream_t st, const char* desc);
 void prof_after(cudaStream_t st);
 struct ProfScope {      // RAII: events around one launch when the profiler is on
   cudaStream_t st; bool on;
-  ProfScope(int cls, double work, cudaStream_t s) : st(s), on(prof_enabled()) { if (on) prof_before(cls, work, s); }
+  ProfScope(int cls, double work, cudaStream_t s, const char* desc = nullptr) : st(s), on(prof_enabled()) { if (on) prof_before(cls, work, s, desc); }
   ~ProfScope() { if (on) prof_after(st); }
 };
 
@@ -48,9 +48,23 @@ struct ProfScope {      // RAII: events around one launch when the profiler is o
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ---- device math
+// exact-erf GELU with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): 1 rcp + 1 ex2 + 6 fma instead of
+// the multi-branch libdevice erff, which dominated the GEMM epilogue
+__device__ __forceinline__ float gelu_erf(float v) {
+  const float z = fabsf(v) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * __expf(-z * z);
+  const float erf_v = copysignf(erf_abs, v);
+  return 0.5f * v * (1.0f + erf_v);
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
-    case PGT_ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+    case PGT_ACT_GELU: return gelu_erf(v);
     case PGT_ACT_SILU: return v / (1.0f + __expf(-v));
     case PGT_ACT_LRELU02: return v > 0.f ? v : 0.2f * v;
     case PGT_ACT_RELU: return fmaxf(v, 0.f);

@@ -2,10 +2,14 @@
 //
 //   out[rows, N] = epilogue( A[rows, K] * W[N, K]^T )          bf16 operands, fp32 accumulate in TMEM
 //
-// One persistent, warp-specialised kernel (192 threads):
+// One persistent, warp-specialised kernel (320 threads):
 //   warp 0      TMA producer: A tile (128 rows x 64 K) and W tile (BN rows x 64 K) per k-block, 128B swizzle
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, cta_group::1)
-//   warps 2..5  epilogue: tcgen05.ld (32x32b) -> bias / activation / residual / SFT -> global store
+//   warps 2..9  epilogue, two warps per TMEM lane quadrant (each half-group of 4 warps owns half of the tile's
+//               column panels): tcgen05.ld -> +bias (smem) -> activation -> +residual -> bf16/fp32 pack into a
+//               128B-swizzled smem staging panel -> TMA store.  The residual panel is TMA-loaded INTO the
+//               staging slot ahead of time, so both the residual read and the output write are full-line,
+//               coalesced bulk copies issued by one thread.
 // Pipelines: smem full/empty ring (TMA <-> MMA) and a 2-deep TMEM accumulator ring (MMA <-> epilogue), so
 // the epilogue of tile i overlaps the main loop of tile i+1.
 //
@@ -16,6 +20,7 @@
 //            is exactly the conv zero padding — no im2col buffer, no halo handling in software
 //   CONV_S2  5-D map [2C, W/2, 2, H/2, F] (row / column parity split) for stride-2 convs
 #include <cudaTypedefs.h>
+#include <cstdio>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -24,8 +29,11 @@ namespace pgt {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int PANEL_BYTES = BM * 128;            // one staging panel: 128 rows x 128 B
+constexpr int NUM_SLOTS = 4;                     // staging slots (two per epilogue half-group)
 
 enum { MODE_LINEAR = 0, MODE_CONV_S1 = 1, MODE_CONV_S2 = 2 };
 
@@ -38,6 +46,8 @@ struct GemmParams {
   int tw, th, tn, tiles_x, tiles_y;
   int cin_blocks, ksize, pad_lo, cin_ld;
   // epilogue
+  int fast_epi;          // 1: smem-staged TMA-store path, 0: direct per-thread global path
+  int has_res_map;       // fast path: residual is TMA-loaded through tmR
   const float* bias;
   int act, epi_mode;
   const void* residual;
@@ -54,9 +64,11 @@ template <int BN>
 struct GemmCfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
-  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGING_BYTES = NUM_SLOTS * PANEL_BYTES;
+  static constexpr int BUDGET = 232448 - 1024 /*align*/ - STAGING_BYTES - 2 * BN * 4 /*bias*/ - 256 /*barriers*/;
+  static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 6 ? 6 : (BUDGET / STAGE_BYTES);
+  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 2 * BN * 4 + 256 + 1024;
 };
 
 __device__ __forceinline__ void decode_conv_tile(const GemmParams& p, int m_blk, int& n0, int& y0, int& x0) {
@@ -69,9 +81,36 @@ __device__ __forceinline__ void decode_conv_tile(const GemmParams& p, int m_blk,
   n0 = tf * p.tn;
 }
 
+__device__ __forceinline__ void act_chunk(float (&f)[32], int act) {
+  switch (act) {                                  // hoisted: one switch per 32-value chunk
+    case PGT_ACT_GELU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+      break;
+    case PGT_ACT_SILU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
+      break;
+    case PGT_ACT_LRELU02:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.2f * f[j]);
+      break;
+    case PGT_ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+      break;
+    case PGT_ACT_SIGMOID:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = 1.0f / (1.0f + __expf(-f[j]));
+      break;
+    default: break;
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -79,12 +118,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;                 // 1024-aligned (all stage sizes are)
+  float* bias_s = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES);   // [2][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 2 * BN);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* res_bar = bars + 2 * STAGES + 4;                           // [2], one per epilogue half-group
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -93,13 +135,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.fast_epi) tma_prefetch_desc(&tmO);
+    if (p.has_res_map) tma_prefetch_desc(&tmR);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], EPI_WARPS * 32);
+      mbar_init(&res_bar[i], 1);
     }
     fence_barrier_init();
   }
@@ -178,133 +223,221 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    const int ew = warp - 2;                   // 0..7
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;                  // half-group: 4 warps covering all 128 rows
     const int r = quad * 32 + lane;            // row of the 128-row tile
+    const int et = threadIdx.x - 64;           // 0..255
+    const bool leader = ((ew & 3) == 0) && lane == 0;
+    const int bar_id = 1 + half;
+    uint32_t res_phase = 0;
+    const int esize = (p.out_dtype == PGT_BF16) ? 2 : 4;
+    const int PW = 128 / esize;                // columns per staging panel
+    const int panels_total = BN / PW;
+    uint8_t* my_slots = staging + half * 2 * PANEL_BYTES;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int n_blk = tile % p.n_tiles;
       const int m_blk = tile / p.n_tiles;
-      bool valid;
-      long long orow;                          // output row (pixel / token) index
-      int pn = 0, py = 0, px = 0;
-      if (p.mode == MODE_LINEAR) {
-        orow = (long long)m_blk * BM + r;
-        valid = orow < p.M;
-      } else {
-        int n0, y0, x0;
-        decode_conv_tile(p, m_blk, n0, y0, x0);
-        const int ix = r % p.tw;
-        const int t2 = r / p.tw;
-        const int iy = t2 % p.th;
-        const int in = t2 / p.th;
-        pn = n0 + in; py = y0 + iy; px = x0 + ix;
-        valid = (pn < p.F) && (py < p.H) && (px < p.W);
-        orow = ((long long)pn * p.H + py) * p.W + px;
-      }
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
       const int col_base = n_blk * BN;
+      int n0 = 0, y0 = 0, x0 = 0;
+      if (p.mode != MODE_LINEAR) decode_conv_tile(p, m_blk, n0, y0, x0);
+      // bias slice of this tile -> smem (double-buffered by tile parity), one 256-thread barrier
+      float* bs = bias_s + (it & 1) * BN;
+      if (et < BN) bs[et] = (p.bias != nullptr && col_base + et < p.N) ? __ldg(p.bias + col_base + et) : 0.f;
+      named_bar_sync(3, EPI_WARPS * 32);
+      const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
+
+      if (p.fast_epi) {
+        const int rounds = (panels_total + NUM_SLOTS - 1) / NUM_SLOTS;
+        for (int rd = 0; rd < rounds; ++rd) {
+          // slot s of half-group h holds panel rd*4 + 2*s + h (interleaved so both half-groups stay busy)
+          const int panel0 = rd * NUM_SLOTS + half;
+          int npan = 0;
+          for (int s = 0; s < 2; ++s) {
+            const int pnl = panel0 + 2 * s;
+            if (pnl < panels_total && col_base + pnl * PW < p.N) npan = s + 1;   // columns beyond N are clipped anyway
+          }
+          if (leader) {
+            bulk_wait_read0();                                 // earlier stores have finished reading my slots
+            if (p.has_res_map && npan > 0) {
+              mbar_arrive_expect_tx(&res_bar[half], npan * PANEL_BYTES);
+              for (int s = 0; s < npan; ++s) {
+                const int c = col_base + (panel0 + 2 * s) * PW;
+                if (p.mode == MODE_LINEAR) tma_load_2d(my_slots + s * PANEL_BYTES, &tmR, &res_bar[half], c, m_blk * BM);
+                else tma_load_4d(my_slots + s * PANEL_BYTES, &tmR, &res_bar[half], c, x0, y0, n0);
+              }
+            }
+          }
+          named_bar_sync(bar_id, 128);                         // slots are free (and residual loads in flight)
+          if (rd == 0) {
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+          }
+          if (p.has_res_map && npan > 0) {
+            mbar_wait(&res_bar[half], res_phase);
+            res_phase ^= 1;
+          }
+          for (int s = 0; s < npan; ++s) {
+            uint8_t* srow = my_slots + s * PANEL_BYTES + r * 128;
+            const int pcol = (panel0 + 2 * s) * PW;            // first column of the panel inside the tile
+            const int nsub = PW / 32;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (col_base + c0 >= p.N) break;       // warp-uniform
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + c0, v);
-        tmem_ld_wait();
-        if (valid) {
-        const int col0 = col_base + c0;
-        const int ncol = min(32, p.N - col0);
-        float f[32];
+            for (int sub = 0; sub < nsub; ++sub) {
+              uint32_t v[32];
+              tmem_ld_32x32(t_row + pcol + sub * 32, v);
+              tmem_ld_wait();
+              float f[32];
+              const float4* b4 = reinterpret_cast<const float4*>(bs + pcol + sub * 32);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncol) f[j] += __ldg(p.bias + col0 + j);
-        }
-        if (p.act != PGT_ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
-        }
-        const bool vec_ok = (ncol == 32);
-        if (p.residual != nullptr) {
-          if (p.res_dtype == PGT_BF16) {
-            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + orow * p.ldr + col0;
-            const bool rvec = vec_ok && ((p.ldr & 7) == 0);
-            float rr[32];
-            if (rvec) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + q);
-                float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-                rr[q * 8 + 0] = a.x; rr[q * 8 + 1] = a.y; rr[q * 8 + 2] = b.x; rr[q * 8 + 3] = b.y;
-                rr[q * 8 + 4] = c.x; rr[q * 8 + 5] = c.y; rr[q * 8 + 6] = d.x; rr[q * 8 + 7] = d.y;
+              for (int q = 0; q < 8; ++q) {
+                const float4 bb = b4[q];
+                f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + bb.x;
+                f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb.y;
+                f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb.z;
+                f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb.w;
               }
-            } else {
+              if (p.act != PGT_ACT_NONE) act_chunk(f, p.act);
+              if (esize == 2) {
+                // 32 bf16 = 64 B = chunks (sub*4 .. sub*4+3) of the 128 B swizzled row
 #pragma unroll
-              for (int j = 0; j < 32; ++j) rr[j] = (j < ncol) ? __bfloat162float(rp[j]) : 0.f;
-            }
-            if (p.epi_mode == PGT_EPI_SFT) {
-              const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(p.aux) + orow * p.ldaux + col0;
+                for (int q = 0; q < 4; ++q) {
+                  uint4* dst = reinterpret_cast<uint4*>(srow + ((((sub << 2) + q) ^ (r & 7)) << 4));
+                  if (p.has_res_map) {
+                    const uint4 u = *dst;
+                    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+                    f[8 * q + 0] += a.x; f[8 * q + 1] += a.y; f[8 * q + 2] += b.x; f[8 * q + 3] += b.y;
+                    f[8 * q + 4] += c.x; f[8 * q + 5] += c.y; f[8 * q + 6] += d.x; f[8 * q + 7] += d.y;
+                  }
+                  uint4 o;
+                  o.x = pack_bf16x2(f[8 * q + 0], f[8 * q + 1]);
+                  o.y = pack_bf16x2(f[8 * q + 2], f[8 * q + 3]);
+                  o.z = pack_bf16x2(f[8 * q + 4], f[8 * q + 5]);
+                  o.w = pack_bf16x2(f[8 * q + 6], f[8 * q + 7]);
+                  *dst = o;
+                }
+              } else {
+                // 32 fp32 = 128 B = the whole swizzled row (nsub == 1)
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float s = (j < ncol) ? __bfloat162float(ap[j]) : 0.f;
-                f[j] = rr[j] + p.sft_w * (rr[j] * s + f[j]);
+                for (int q = 0; q < 8; ++q) {
+                  float4* dst = reinterpret_cast<float4*>(srow + ((q ^ (r & 7)) << 4));
+                  float4 o = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                  if (p.has_res_map) {
+                    const float4 u = *dst;
+                    o.x += u.x; o.y += u.y; o.z += u.z; o.w += u.w;
+                  }
+                  *dst = o;
+                }
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] += rr[j];
             }
-          } else {
-            const float* rp = reinterpret_cast<const float*>(p.residual) + orow * p.ldr + col0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncol) f[j] += __ldg(rp + j);
+          }
+          fence_proxy_async();                                 // generic smem writes -> visible to the TMA engine
+          named_bar_sync(bar_id, 128);
+          if (leader) {
+            for (int s = 0; s < npan; ++s) {
+              const int c = col_base + (panel0 + 2 * s) * PW;
+              if (p.mode == MODE_LINEAR) tma_store_2d(&tmO, my_slots + s * PANEL_BYTES, c, m_blk * BM);
+              else tma_store_4d(&tmO, my_slots + s * PANEL_BYTES, c, x0, y0, n0);
+            }
+            bulk_commit();
           }
         }
-        if (p.out_layout == PGT_OUT_NCHW) {
-          float* op = reinterpret_cast<float*>(p.out);
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncol) op[(((long long)pn * p.N + (col0 + j)) * p.H + py) * p.W + px] = f[j];
-        } else if (p.out_dtype == PGT_BF16) {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col0;
-          if (vec_ok && ((p.ldo & 7) == 0)) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 u;
-              u.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
-              u.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
-              u.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
-              u.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
-              reinterpret_cast<uint4*>(op)[q] = u;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncol) op[j] = __float2bfloat16_rn(f[j]);
-          }
+      } else {
+        // ---------------- direct path (SFT epilogue, NCHW fp32 output, unaligned views): per-thread global I/O
+        bool valid;
+        long long orow;
+        int pn = 0, py = 0, px = 0;
+        if (p.mode == MODE_LINEAR) {
+          orow = (long long)m_blk * BM + r;
+          valid = orow < p.M;
         } else {
-          float* op = reinterpret_cast<float*>(p.out) + orow * p.ldo + col0;
-          if (vec_ok && ((p.ldo & 3) == 0)) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              reinterpret_cast<float4*>(op)[q] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncol) op[j] = f[j];
-          }
+          const int ix = r % p.tw;
+          const int t2 = r / p.tw;
+          const int iy = t2 % p.th;
+          const int in = t2 / p.th;
+          pn = n0 + in; py = y0 + iy; px = x0 + ix;
+          valid = (pn < p.F) && (py < p.H) && (px < p.W);
+          orow = ((long long)pn * p.H + py) * p.W + px;
         }
-        }  // valid
-        __syncwarp();
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const int c_lo = half * (BN / 2), c_hi = c_lo + BN / 2;
+#pragma unroll 1
+        for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+          if (col_base + c0 >= p.N) break;       // warp-uniform
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + c0, v);
+          tmem_ld_wait();
+          if (valid) {
+            const int col0 = col_base + c0;
+            const int ncol = min(32, p.N - col0);
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bs[c0 + j];
+            if (p.act != PGT_ACT_NONE) act_chunk(f, p.act);
+            if (p.residual != nullptr) {
+              if (p.res_dtype == PGT_BF16) {
+                const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + orow * p.ldr + col0;
+                float rr[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) rr[j] = (j < ncol) ? __bfloat162float(rp[j]) : 0.f;
+                if (p.epi_mode == PGT_EPI_SFT) {
+                  const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(p.aux) + orow * p.ldaux + col0;
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) {
+                    const float sc = (j < ncol) ? __bfloat162float(ap[j]) : 0.f;
+                    f[j] = rr[j] + p.sft_w * (rr[j] * sc + f[j]);
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) f[j] += rr[j];
+                }
+              } else {
+                const float* rp = reinterpret_cast<const float*>(p.residual) + orow * p.ldr + col0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncol) f[j] += __ldg(rp + j);
+              }
+            }
+            if (p.out_layout == PGT_OUT_NCHW) {
+              float* op = reinterpret_cast<float*>(p.out);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncol) op[(((long long)pn * p.N + (col0 + j)) * p.H + py) * p.W + px] = f[j];
+            } else if (p.out_dtype == PGT_BF16) {
+              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col0;
+              if (ncol == 32 && ((p.ldo & 7) == 0)) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  uint4 u;
+                  u.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
+                  u.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
+                  u.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
+                  u.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+                  reinterpret_cast<uint4*>(op)[q] = u;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncol) op[j] = __float2bfloat16_rn(f[j]);
+              }
+            } else {
+              float* op = reinterpret_cast<float*>(p.out) + orow * p.ldo + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncol) op[j] = f[j];
+            }
+          }
+          __syncwarp();
+        }
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
     }
+    if (p.fast_epi && leader) bulk_wait0();      // all output bytes written before the CTA retires
   }
 
   tc_fence_before();
@@ -332,7 +465,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box) {
+                      const uint32_t* box, int dtype = PGT_BF16) {
   auto fn = get_encode_fn();
   if (fn == nullptr) return PGT_ERR_DRIVER;
   cuuint64_t gdim[5];
@@ -345,23 +478,61 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64
     estr[i] = 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, dtype == PGT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank,
+                  const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? PGT_OK : PGT_ERR_DRIVER;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Output-space tensor map ([N, rows] or [N, W, H, F]) with a 128-byte-wide panel box, for TMA stores of the
+// result and TMA loads of the residual.
+static int encode_out_map(CUtensorMap* map, const GemmParams& p, const void* base, int ld, int dtype) {
+  const int esize = dtype == PGT_BF16 ? 2 : 4;
+  const uint32_t pw = 128 / esize;
+  if (p.mode == MODE_LINEAR) {
+    uint64_t dims[2] = {(uint64_t)p.N, (uint64_t)p.M};
+    uint64_t str[1] = {(uint64_t)ld * esize};
+    uint32_t box[2] = {pw, BM};
+    return encode_map(map, base, 2, dims, str, box, dtype);
+  }
+  uint64_t dims[4] = {(uint64_t)p.N, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.F};
+  uint64_t str[3] = {(uint64_t)ld * esize, (uint64_t)p.W * ld * esize, (uint64_t)p.H * p.W * ld * esize};
+  uint32_t box[4] = {pw, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
+  return encode_map(map, base, 4, dims, str, box, dtype);
 }
 
 template <int BN>
 static int launch_gemm(const CUtensorMap& tmA, const void* W, int ldw, GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  CUtensorMap tmB;
+  static_assert(Cfg::STAGES >= 3, "pipeline too shallow");
+  CUtensorMap tmB, tmO, tmR;
   {
-    // rows beyond N (weight matrices are packed to a multiple of 16 rows, not of BN) are zero-filled
+    // rows beyond N (weight matrices are not padded to BN rows) are zero-filled by TMA
     uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
     uint64_t str[1] = {(uint64_t)ldw * 2};
     uint32_t box[2] = {BK, (uint32_t)BN};
     int rc = encode_map(&tmB, W, 2, dims, str, box);
     if (rc != PGT_OK) return rc;
+  }
+  const int esize = p.out_dtype == PGT_BF16 ? 2 : 4;
+  p.fast_epi = (p.out_layout == PGT_OUT_NHWC && p.epi_mode == PGT_EPI_PLAIN && aligned16(p.out) &&
+                ((long long)p.ldo * esize) % 16 == 0) ? 1 : 0;
+  p.has_res_map = 0;
+  if (p.fast_epi && p.residual != nullptr) {
+    if (p.res_dtype == p.out_dtype && aligned16(p.residual) && ((long long)p.ldr * esize) % 16 == 0) p.has_res_map = 1;
+    else p.fast_epi = 0;
+  }
+  tmO = tmA;
+  tmR = tmA;                                       // placeholders when unused (never dereferenced)
+  if (p.fast_epi) {
+    int rc = encode_out_map(&tmO, p, p.out, p.ldo, p.out_dtype);
+    if (rc != PGT_OK) return rc;
+    if (p.has_res_map) {
+      rc = encode_out_map(&tmR, p, p.residual, p.ldr, p.res_dtype);
+      if (rc != PGT_OK) return rc;
+    }
   }
   p.n_tiles = ceil_div(p.N, BN);
   static bool attr_set = false;
@@ -372,15 +543,19 @@ static int launch_gemm(const CUtensorMap& tmA, const void* W, int ldw, GemmParam
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   {
-    ProfScope ps(PGT_PROF_GEMM, p.flops, stream);
-    gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    char desc[96];
+    if (prof_enabled()) {
+      if (p.mode == MODE_LINEAR) snprintf(desc, sizeof(desc), "linear M%d N%d K%d BN%d e%d", p.M, p.N, p.K, BN, p.fast_epi);
+      else snprintf(desc, sizeof(desc), "conv%d s%d F%d H%d W%d K%d N%d BN%d t%dx%dx%d e%d", p.ksize, p.mode, p.F, p.H, p.W, p.K, p.N, BN, p.tn, p.th, p.tw, p.fast_epi);
+    }
+    ProfScope ps(PGT_PROF_GEMM, p.flops, stream, desc);
+    gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, tmR, p);
   }
   PGT_LAUNCH_OK();
   return PGT_OK;
 }
 
 static int pick_bn(int N, int m_tiles) {
-  if (N <= 32) return 32;
   if (N <= 64) return 64;
   if (N <= 128) return 128;
   // wide N: prefer 256-wide tiles when they still fill the machine
@@ -390,7 +565,6 @@ static int pick_bn(int N, int m_tiles) {
 
 static int dispatch_gemm(const CUtensorMap& tmA, const void* W, int ldw, GemmParams& p, cudaStream_t stream) {
   switch (pick_bn(p.N, p.m_tiles)) {
-    case 32: return launch_gemm<32>(tmA, W, ldw, p, stream);
     case 64: return launch_gemm<64>(tmA, W, ldw, p, stream);
     case 128: return launch_gemm<128>(tmA, W, ldw, p, stream);
     default: return launch_gemm<256>(tmA, W, ldw, p, stream);
@@ -417,8 +591,6 @@ static int fill_epilogue(GemmParams& p, const pgt_epilogue* ep) {
   if (p.out_layout == PGT_OUT_NCHW && (p.out_dtype != PGT_F32 || p.mode == MODE_LINEAR)) return PGT_ERR_INVALID;
   return PGT_OK;
 }
-
-static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace pgt
 

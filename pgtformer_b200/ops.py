@@ -227,9 +227,13 @@ def profile_begin():
     L.check(L.load().pgt_profile_begin())
 
 
-def profile_end():
-    """-> {class: (work, ms, launches)}; work is FLOPs (gemm/attention/argmin) or bytes (argmax/norm)."""
+def profile_end(csv_path=None):
+    """-> {class: (work, ms, launches)}; work is FLOPs (gemm/attention/argmin) or bytes (argmax/norm).
+    With csv_path, one row per launch is written there as well."""
     n = len(PROF_CLASSES)
     work, ms, cnt = (ctypes.c_double * n)(), (ctypes.c_double * n)(), (ctypes.c_int64 * n)()
-    L.check(L.load().pgt_profile_end(work, ms, cnt))
+    if csv_path is None:
+        L.check(L.load().pgt_profile_end(work, ms, cnt))
+    else:
+        L.check(L.load().pgt_profile_end_csv(csv_path.encode(), work, ms, cnt))
     return {PROF_CLASSES[i]: (work[i], ms[i], int(cnt[i])) for i in range(n)}

@@ -81,6 +81,23 @@ def test_linear(M, N, K, act, res, out_dt):
     check_close(out, ref, 'linear', bf16_out=(out_dt == torch.bfloat16))
 
 
+@pytest.mark.parametrize('M,N,K', [(1000, 512, 512), (3072, 1024, 512), (130, 96, 64)])
+def test_linear_fp32_residual_stream(M, N, K):
+    """fp32 residual + fp32 output (global transformer): residual TMA-loaded into the staging slot."""
+    o = ops()
+    a, w, b = bf(rnd((M, K), 1)), bf(rnd((N, K), 2, K ** -0.5)), rnd((N,), 3, 0.1)
+    r = rnd((M, N), 4)
+    out = torch.empty(M, N, dtype=torch.float32, device=DEV)
+    o.linear(a.to(DEV), w.to(DEV), out, bias=b.to(DEV), residual=r.to(DEV))
+    torch.cuda.synchronize()
+    check_close(out, a.float() @ w.float().t() + b + r, 'linear fp32 residual')
+    # in-place residual stream (out aliases residual), as the engine may do
+    rr = r.to(DEV).clone()
+    o.linear(a.to(DEV), w.to(DEV), rr, bias=b.to(DEV), residual=rr)
+    torch.cuda.synchronize()
+    check_close(rr, a.float() @ w.float().t() + b + r, 'linear in-place residual')
+
+
 def test_linear_k_tail_and_strided_views():
     """K = 57 (convpos) inside a 64-wide buffer; output into a channel slice of a wider buffer."""
     o = ops()
