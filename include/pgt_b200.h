@@ -70,7 +70,7 @@ void pgt_reset_launch_count(void);
  * per class, the summed algorithmic work (FLOPs, or bytes for the HBM-bound classes), the summed
  * device time in ms and the launch count.  Arrays have PGT_PROF_CLASSES entries. */
 enum { PGT_PROF_GEMM = 0, PGT_PROF_WINDOW_ATTN = 1, PGT_PROF_MHA = 2, PGT_PROF_ARGMAX = 3, PGT_PROF_ARGMIN = 4,
-       PGT_PROF_NORM = 5, PGT_PROF_MOVE = 6, PGT_PROF_CLASSES = 8 };
+       PGT_PROF_NORM = 5, PGT_PROF_MOVE = 6, PGT_PROF_LAYERNORM = 7, PGT_PROF_CLASSES = 8 };
 int pgt_profile_begin(void);
 int pgt_profile_end(double* work, double* ms, int64_t* launches);
 /* same, and also writes one CSV row per launch (class, description, work, ms) to `path` (host string). */
@@ -95,6 +95,16 @@ int pgt_linear_bf16(const void* A, int lda, const void* W, int ldw, int M, int N
  * (archs/tdcrqvae3_arch.py:45-52,67-76), conv_in/conv_out, and the BiSeNet convs. */
 int pgt_conv_bf16(const void* x, int F, int Hin, int Win, int Cin, int ldx, const void* Wp, int ldw,
                   int Cout, int ksize, int stride, int pad_lo, const pgt_epilogue* ep, void* stream);
+
+/* ---- nearest-x2 upsample + 3x3 conv as ONE op, without materialising the upsampled tensor: the output
+ * pixel (2y+py, 2x+px) only sees a 2x2 neighbourhood of the source, so the op is four 2x2 convolutions
+ * (one per output phase) over the SOURCE resolution with tap-summed weights: 4/9 of the FLOPs, 1/4 of the
+ * A traffic.  Wp4: bf16 [4 phases][Cout][4*CinPad], phase = py*2+px, K index = (ty*2+tx)*CinPad + c, where
+ * taps of phase p are the sums w[Sy(ty), Sx(tx)] with S(0) = {0} / {0,1} and S(1) = {1,2} / {2} for p = 0 / 1
+ * (packed by pgtformer_b200/engine.py::_pack_up2x).  ep->out is the [F, 2Hin, 2Win, Cout] result.
+ * Replaces Upsample.forward (archs/tdcrqvae3_arch.py:45-52). */
+int pgt_conv_up2x_bf16(const void* x, int F, int Hin, int Win, int Cin, int ldx, const void* Wp4, int ldw,
+                       int Cout, const pgt_epilogue* ep, void* stream);
 
 /* ---- first conv of the encoder: 3x3, Cin=3, fp32 NCHW input -> NHWC bf16 (direct FFMA kernel;
  * K = 27 is too small for the tensor pipe).  w: fp32 [Cout,3,3,3] (OIHW), bias fp32 [Cout].

@@ -21,6 +21,7 @@
 //   CONV_S2  5-D map [2C, W/2, 2, H/2, F] (row / column parity split) for stride-2 convs
 #include <cudaTypedefs.h>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -45,7 +46,10 @@ struct GemmParams {
   int F, H, W;
   int tw, th, tn, tiles_x, tiles_y;
   int cin_blocks, ksize, pad_lo, cin_ld;
+  int pad_x, pad_y;            // CONV_S1: zero columns / rows before the first input column / row
+  long long o_sx, o_sy, o_sf;  // output element strides of the (x, y, frame) dims (strided placement for up2x)
   // epilogue
+  int b_resident;        // halo conv: all 9 weight blocks fit the B ring -> loaded once per CTA, never recycled
   int fast_epi;          // 1: smem-staged TMA-store path, 0: direct per-thread global path
   int has_res_map;       // fast path: residual is TMA-loaded through tmR
   const float* bias;
@@ -107,11 +111,294 @@ __device__ __forceinline__ void act_chunk(float (&f)[32], int act) {
   }
 }
 
+// ------------------------------------------------------------------------------------------- epilogue
+// Shared by the GEMM/conv kernel and the halo-reuse conv kernel.  Runs on warps 2..9 (256 threads).
+struct EpiCtx {
+  uint8_t* staging;        // NUM_SLOTS x PANEL_BYTES, 1024-aligned
+  float* bias_s;           // [2][BN]
+  uint64_t* tmem_full;     // [2]
+  uint64_t* tmem_empty;    // [2]
+  uint64_t* res_bar;       // [2]
+  uint32_t tmem_base;
+};
+
+// One 32-column chunk of a staging panel: TMEM -> +bias -> act -> (+residual | SFT) -> packed into the swizzled row.
+template <bool kSft>
+__device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, const float* bias32, uint8_t* srow,
+                                          int r, int sub, int esize, bool has_res) {
+  uint32_t v[32];
+  tmem_ld_32x32(taddr, v);
+  tmem_ld_wait();
+  float f[32];
+  const float4* b4 = reinterpret_cast<const float4*>(bias32);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 bb = b4[q];
+    f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + bb.x;
+    f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb.y;
+    f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb.z;
+    f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb.w;
+  }
+  if (p.act != PGT_ACT_NONE) act_chunk(f, p.act);
+  if (esize == 2) {
+    // 32 bf16 = 64 B = chunks (sub*4 .. sub*4+3) of the 128 B swizzled row
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int off = ((((sub << 2) + q) ^ (r & 7)) << 4);
+      uint4* dst = reinterpret_cast<uint4*>(srow + off);
+      if (has_res) {
+        const uint4 u = *dst;
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        const float rr[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+        if (kSft) {
+          const uint4 ux = *reinterpret_cast<const uint4*>(srow + PANEL_BYTES + off);
+          const float2 sa = unpack_bf16x2(ux.x), sb = unpack_bf16x2(ux.y), sc = unpack_bf16x2(ux.z), sd = unpack_bf16x2(ux.w);
+          const float ss[8] = {sa.x, sa.y, sb.x, sb.y, sc.x, sc.y, sd.x, sd.y};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[8 * q + e] = rr[e] + p.sft_w * (rr[e] * ss[e] + f[8 * q + e]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[8 * q + e] += rr[e];
+        }
+      }
+      uint4 o;
+      o.x = pack_bf16x2(f[8 * q + 0], f[8 * q + 1]);
+      o.y = pack_bf16x2(f[8 * q + 2], f[8 * q + 3]);
+      o.z = pack_bf16x2(f[8 * q + 4], f[8 * q + 5]);
+      o.w = pack_bf16x2(f[8 * q + 6], f[8 * q + 7]);
+      *dst = o;
+    }
+  } else {
+    // 32 fp32 = 128 B = the whole swizzled row
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float4* dst = reinterpret_cast<float4*>(srow + ((q ^ (r & 7)) << 4));
+      float4 o = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+      if (has_res) {
+        const float4 u = *dst;
+        o.x += u.x; o.y += u.y; o.z += u.z; o.w += u.w;
+      }
+      *dst = o;
+    }
+  }
+}
+
+// Epilogue work is a stream of ITEMS = (tile, 128-byte-wide column panel), processed by all 8 epilogue warps
+// together (the two warps of a TMEM lane quadrant split the panel's 32-column chunks).  Items flow through a ring
+// of staging slots: the residual panel of item k+D is TMA-prefetched while item k is converted, and the TMA
+// store of item k drains while items k+1.. are processed, so neither latency sits on the critical path.
+template <int BN>
+__device__ __forceinline__ void epilogue_loop(const GemmParams& p, const EpiCtx& ctx, const CUtensorMap& tmO,
+                                              const CUtensorMap& tmR, const CUtensorMap& tmX, int warp, int lane,
+                                              int num_tiles) {
+  uint8_t* staging = ctx.staging;
+  float* bias_s = ctx.bias_s;
+  uint64_t* tmem_full = ctx.tmem_full;
+  uint64_t* tmem_empty = ctx.tmem_empty;
+  uint64_t* res_bar = ctx.res_bar;             // [NUM_SLOTS]
+  const uint32_t tmem_base = ctx.tmem_base;
+  const int ew = warp - 2;                   // 0..7
+  const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
+  const int half = ew >> 2;                  // which of the quadrant's two warps
+  const int r = quad * 32 + lane;            // row of the 128-row tile
+  const int et = threadIdx.x - 64;           // 0..255
+  const bool leader = (et == 0);
+  const int esize = (p.out_dtype == PGT_BF16) ? 2 : 4;
+  const int PW = 128 / esize;                // columns per staging panel
+  const int nsub = PW / 32;
+  const int panels_total = BN / PW;
+  const bool sft = (p.epi_mode == PGT_EPI_SFT);
+  const int S = sft ? 2 : 1;                 // staging slots per item (SFT: residual/out + scale)
+  const int R = NUM_SLOTS / S;               // ring length in items
+  const int D = R / 2;                       // residual prefetch distance in items
+
+  // number of panels of tile `t` whose first column is inside N
+  auto panels_in_tile = [&](int t) {
+    const int cb = (t % p.n_tiles) * BN;
+    int n = (p.N - cb + PW - 1) / PW;
+    return n > panels_total ? panels_total : n;
+  };
+  // leader only: TMA-load the residual (and SFT scale) panel of item (t, pnl) into ring position `pos`
+  auto issue_res_load = [&](int t, int pnl, int pos) {
+    const int nb = t % p.n_tiles, mb = t / p.n_tiles;
+    const int c = nb * BN + pnl * PW;
+    uint8_t* dst = staging + pos * S * PANEL_BYTES;
+    uint64_t* bar = &res_bar[pos];
+    mbar_arrive_expect_tx(bar, S * PANEL_BYTES);
+    if (p.mode == MODE_LINEAR) {
+      tma_load_2d(dst, &tmR, bar, c, mb * BM);
+      if (sft) tma_load_2d(dst + PANEL_BYTES, &tmX, bar, c, mb * BM);
+    } else {
+      int n0, y0, x0;
+      decode_conv_tile(p, mb, n0, y0, x0);
+      tma_load_4d(dst, &tmR, bar, c, x0, y0, n0);
+      if (sft) tma_load_4d(dst + PANEL_BYTES, &tmX, bar, c, x0, y0, n0);
+    }
+  };
+  // advance (t, pnl) by `n` items in this CTA's item stream; false when the stream ends first
+  auto advance = [&](int& t, int& pnl, int n) -> bool {
+    while (n > 0) {
+      if (t >= num_tiles) return false;
+      ++pnl;
+      if (pnl >= panels_in_tile(t)) { t += gridDim.x; pnl = 0; }
+      --n;
+    }
+    return t < num_tiles;
+  };
+
+  int k = 0;                                 // item counter
+  if (p.fast_epi && p.has_res_map && leader) {
+    int t = blockIdx.x, pnl = 0;
+    for (int d = 0; d < D && t < num_tiles; ++d) {
+      issue_res_load(t, pnl, d % R);
+      if (!advance(t, pnl, 1)) break;
+    }
+  }
+  int it = 0;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    const int acc = it & 1;
+    const uint32_t acc_phase = (it >> 1) & 1;
+    const int n_blk = tile % p.n_tiles;
+    const int m_blk = tile / p.n_tiles;
+    const int col_base = n_blk * BN;
+    int n0 = 0, y0 = 0, x0 = 0;
+    if (p.mode != MODE_LINEAR) decode_conv_tile(p, m_blk, n0, y0, x0);
+    // bias slice of this tile -> smem (double-buffered by tile parity), one 256-thread barrier
+    float* bs = bias_s + (it & 1) * BN;
+    if (et < BN) bs[et] = (p.bias != nullptr && col_base + et < p.N) ? __ldg(p.bias + col_base + et) : 0.f;
+    named_bar_sync(3, EPI_WARPS * 32);
+    const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
+
+    if (p.fast_epi) {
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int npan = panels_in_tile(tile);
+      for (int pnl = 0; pnl < npan; ++pnl, ++k) {
+        const int pos = k % R;
+        if (leader) {
+          // ring position of item k+D was last used by item k+D-R: all but the newest D-1 stores must have been read
+          if (D == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+          if (p.has_res_map) {
+            int nt = tile, npnl = pnl;
+            if (advance(nt, npnl, D)) issue_res_load(nt, npnl, (k + D) % R);
+          }
+        }
+        if (p.has_res_map) mbar_wait(&res_bar[pos], (k / R) & 1);
+        uint8_t* srow = staging + pos * S * PANEL_BYTES + r * 128;
+        const int pcol = pnl * PW;
+        for (int sub = half; sub < nsub; sub += 2) {
+          if (sft) epi_chunk<true>(p, t_row + pcol + sub * 32, bs + pcol + sub * 32, srow, r, sub, esize, true);
+          else epi_chunk<false>(p, t_row + pcol + sub * 32, bs + pcol + sub * 32, srow, r, sub, esize, p.has_res_map != 0);
+        }
+        fence_proxy_async();                 // generic smem writes -> visible to the TMA engine
+        named_bar_sync(4, EPI_WARPS * 32);   // item complete (also orders ring reuse R items later)
+        if (leader) {
+          const int c = col_base + pcol;
+          if (p.mode == MODE_LINEAR) tma_store_2d(&tmO, staging + pos * S * PANEL_BYTES, c, m_blk * BM);
+          else tma_store_4d(&tmO, staging + pos * S * PANEL_BYTES, c, x0, y0, n0);
+          bulk_commit();
+        }
+      }
+    } else {
+      // ---------------- direct path (NCHW fp32 output, unaligned views, mixed residual dtype): per-thread global I/O
+      bool valid;
+      long long orow;
+      int pn = 0, py = 0, px = 0;
+      if (p.mode == MODE_LINEAR) {
+        orow = (long long)m_blk * BM + r;
+        valid = orow < p.M;
+      } else {
+        const int ix = r % p.tw;
+        const int t2 = r / p.tw;
+        const int iy = t2 % p.th;
+        const int in = t2 / p.th;
+        pn = n0 + in; py = y0 + iy; px = x0 + ix;
+        valid = (pn < p.F) && (py < p.H) && (px < p.W);
+        orow = ((long long)pn * p.H + py) * p.W + px;
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int c_lo = half * (BN / 2), c_hi = c_lo + BN / 2;
+#pragma unroll 1
+      for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+        if (col_base + c0 >= p.N) break;       // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          const int col0 = col_base + c0;
+          const int ncol = min(32, p.N - col0);
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bs[c0 + j];
+          if (p.act != PGT_ACT_NONE) act_chunk(f, p.act);
+          if (p.residual != nullptr) {
+            if (p.res_dtype == PGT_BF16) {
+              const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + orow * p.ldr + col0;
+              float rr[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) rr[j] = (j < ncol) ? __bfloat162float(rp[j]) : 0.f;
+              if (p.epi_mode == PGT_EPI_SFT) {
+                const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(p.aux) + orow * p.ldaux + col0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const float sc = (j < ncol) ? __bfloat162float(ap[j]) : 0.f;
+                  f[j] = rr[j] + p.sft_w * (rr[j] * sc + f[j]);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] += rr[j];
+              }
+            } else {
+              const float* rp = reinterpret_cast<const float*>(p.residual) + orow * p.ldr + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncol) f[j] += __ldg(rp + j);
+            }
+          }
+          if (p.out_layout == PGT_OUT_NCHW) {
+            float* op = reinterpret_cast<float*>(p.out);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncol) op[(((long long)pn * p.N + (col0 + j)) * p.H + py) * p.W + px] = f[j];
+          } else if (p.out_dtype == PGT_BF16) {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col0;
+            if (ncol == 32 && ((p.ldo & 7) == 0)) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 u;
+                u.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
+                u.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
+                u.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
+                u.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+                reinterpret_cast<uint4*>(op)[q] = u;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncol) op[j] = __float2bfloat16_rn(f[j]);
+            }
+          } else {
+            float* op = reinterpret_cast<float*>(p.out) + orow * p.ldo + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncol) op[j] = f[j];
+          }
+        }
+        __syncwarp();
+      }
+    }
+    tc_fence_before();
+    mbar_arrive(&tmem_empty[acc]);
+  }
+  if (p.fast_epi && leader) bulk_wait0();      // all output bytes written before the CTA retires
+}
+
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -125,8 +412,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
-  uint64_t* res_bar = bars + 2 * STAGES + 4;                           // [2], one per epilogue half-group
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+  uint64_t* res_bar = bars + 2 * STAGES + 4;                           // [2 half-groups][2 slots]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -137,6 +424,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
     if (p.fast_epi) tma_prefetch_desc(&tmO);
     if (p.has_res_map) tma_prefetch_desc(&tmR);
+    if (p.fast_epi && p.epi_mode == PGT_EPI_SFT) tma_prefetch_desc(&tmX);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -144,7 +432,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], EPI_WARPS * 32);
-      mbar_init(&res_bar[i], 1);
+      mbar_init(&res_bar[2 * i], 1);             // res_bar[NUM_SLOTS]: one per staging ring position
+      mbar_init(&res_bar[2 * i + 1], 1);
     }
     fence_barrier_init();
   }
@@ -158,7 +447,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // (whole warp runs the loop and the waits; the copies are issued under elect.sync so that ptxas sees a
+    //  single-lane region and emits the uniform-datapath UTMALDG directly)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -168,6 +459,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.mode != MODE_LINEAR) decode_conv_tile(p, m_blk, n0, y0, x0);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           void* dst_a = smem_a + stage * A_STAGE_BYTES;
           void* dst_b = smem_b + stage * Cfg::B_STAGE_BYTES;
@@ -179,7 +471,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int dy = tap / p.ksize;
             const int dx = tap - dy * p.ksize;
             if (p.mode == MODE_CONV_S1) {
-              tma_load_4d(dst_a, &tmA, &full_bar[stage], cb * BK, x0 + dx - p.pad_lo, y0 + dy - p.pad_lo, n0);
+              tma_load_4d(dst_a, &tmA, &full_bar[stage], cb * BK, x0 + dx - p.pad_x, y0 + dy - p.pad_y, n0);
             } else {
               const int oy = dy - p.pad_lo, ox = dx - p.pad_lo;
               const int qy = (oy < 0) ? -((1 - oy) >> 1) : (oy >> 1);
@@ -189,13 +481,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           tma_load_2d(dst_b, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (one elected lane issues)
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -209,235 +503,181 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
-          const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES));
+          if (elect_one()) {
+            const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
+            const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES));
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // +32 bytes (2 x 16 B units) per UMMA_K=16 step inside the 128 B swizzle row
-            umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // +32 bytes (2 x 16 B units) per UMMA_K=16 step inside the 128 B swizzle row
+              umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);              // frees the smem stage when the MMAs retire
+            if (kb == p.num_kb - 1) umma_commit(&tmem_full[acc]);
           }
-          umma_commit(&empty_bar[stage]);              // frees the smem stage when the MMAs retire
-          if (kb == p.num_kb - 1) umma_commit(&tmem_full[acc]);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9)
-    const int ew = warp - 2;                   // 0..7
-    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
-    const int half = ew >> 2;                  // half-group: 4 warps covering all 128 rows
-    const int r = quad * 32 + lane;            // row of the 128-row tile
-    const int et = threadIdx.x - 64;           // 0..255
-    const bool leader = ((ew & 3) == 0) && lane == 0;
-    const int bar_id = 1 + half;
-    uint32_t res_phase = 0;
-    const int esize = (p.out_dtype == PGT_BF16) ? 2 : 4;
-    const int PW = 128 / esize;                // columns per staging panel
-    const int panels_total = BN / PW;
-    uint8_t* my_slots = staging + half * 2 * PANEL_BYTES;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      const int n_blk = tile % p.n_tiles;
-      const int m_blk = tile / p.n_tiles;
-      const int col_base = n_blk * BN;
-      int n0 = 0, y0 = 0, x0 = 0;
-      if (p.mode != MODE_LINEAR) decode_conv_tile(p, m_blk, n0, y0, x0);
-      // bias slice of this tile -> smem (double-buffered by tile parity), one 256-thread barrier
-      float* bs = bias_s + (it & 1) * BN;
-      if (et < BN) bs[et] = (p.bias != nullptr && col_base + et < p.N) ? __ldg(p.bias + col_base + et) : 0.f;
-      named_bar_sync(3, EPI_WARPS * 32);
-      const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
+    EpiCtx ctx{staging, bias_s, tmem_full, tmem_empty, res_bar, tmem_base};
+    epilogue_loop<BN>(p, ctx, tmO, tmR, tmX, warp, lane, num_tiles);
+  }
 
-      if (p.fast_epi) {
-        const int rounds = (panels_total + NUM_SLOTS - 1) / NUM_SLOTS;
-        for (int rd = 0; rd < rounds; ++rd) {
-          // slot s of half-group h holds panel rd*4 + 2*s + h (interleaved so both half-groups stay busy)
-          const int panel0 = rd * NUM_SLOTS + half;
-          int npan = 0;
-          for (int s = 0; s < 2; ++s) {
-            const int pnl = panel0 + 2 * s;
-            if (pnl < panels_total && col_base + pnl * PW < p.N) npan = s + 1;   // columns beyond N are clipped anyway
-          }
-          if (leader) {
-            bulk_wait_read0();                                 // earlier stores have finished reading my slots
-            if (p.has_res_map && npan > 0) {
-              mbar_arrive_expect_tx(&res_bar[half], npan * PANEL_BYTES);
-              for (int s = 0; s < npan; ++s) {
-                const int c = col_base + (panel0 + 2 * s) * PW;
-                if (p.mode == MODE_LINEAR) tma_load_2d(my_slots + s * PANEL_BYTES, &tmR, &res_bar[half], c, m_blk * BM);
-                else tma_load_4d(my_slots + s * PANEL_BYTES, &tmR, &res_bar[half], c, x0, y0, n0);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------- halo-reuse conv
+// 3x3 stride-1 convolution for narrow outputs (Cout <= 128), where the plain implicit GEMM is bound by
+// L2 -> SM traffic (every tap re-reads its 128x64 A tile: 9x input traffic).  Here the 128-pixel tile is an
+// 8 x 16 patch and, per (dx, 64-channel block), ONE (8+2) x 16 halo slab is loaded; the three dy taps are the
+// same slab viewed at row offsets 0 / 16 / 32 (2048-byte steps, so the 128B-swizzle phase is unchanged and plain
+// UMMA descriptors apply).  A traffic drops from 9 to 3.75 tile-loads per channel block; the weights stream
+// through their own, deeper ring (one BN x 64 block per tap).
+constexpr int HALO_TW = 16, HALO_TH = 8;
+constexpr int HALO_A_BYTES = (HALO_TH + 2) * HALO_TW * 128;
+
+template <int BN>
+struct HaloCfg {
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int A_STAGES = (BN == 64) ? 4 : 3;
+  static constexpr int B_STAGES = (BN == 64) ? 9 : 6;
+  static constexpr int STAGING_BYTES = NUM_SLOTS * PANEL_BYTES;
+  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : 256;
+  static constexpr int SMEM_BYTES = A_STAGES * HALO_A_BYTES + B_STAGES * B_BYTES + STAGING_BYTES + 2 * BN * 4 + 512 + 1024;
+  static_assert(SMEM_BYTES <= 232448, "halo conv smem budget");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
+                 const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
+  using Cfg = HaloCfg<BN>;
+  constexpr int AS = Cfg::A_STAGES, BS = Cfg::B_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + AS * HALO_A_BYTES;
+  uint8_t* staging = smem_b + BS * Cfg::B_BYTES;
+  float* bias_s = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 2 * BN);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + AS;
+  uint64_t* b_full = bars + 2 * AS;
+  uint64_t* b_empty = bars + 2 * AS + BS;
+  uint64_t* tmem_full = bars + 2 * AS + 2 * BS;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* res_bar = tmem_full + 4;                                   // [2 half-groups][2 slots]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int cin_pad = p.cin_blocks * BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.fast_epi) tma_prefetch_desc(&tmO);
+    if (p.has_res_map) tma_prefetch_desc(&tmR);
+    for (int i = 0; i < AS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], EPI_WARPS * 32);
+      mbar_init(&res_bar[2 * i], 1);             // res_bar[NUM_SLOTS]: one per staging ring position
+      mbar_init(&res_bar[2 * i + 1], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.n_tiles;
+        const int m_blk = tile / p.n_tiles;
+        int n0, y0, x0;
+        decode_conv_tile(p, m_blk, n0, y0, x0);
+        for (int cb = 0; cb < p.cin_blocks; ++cb) {
+          for (int dx = 0; dx < 3; ++dx) {
+            mbar_wait(&a_empty[as], aph ^ 1);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&a_full[as], HALO_A_BYTES);
+              tma_load_4d(smem_a + as * HALO_A_BYTES, &tmA, &a_full[as], cb * BK, x0 + dx - 1, y0 - 1, n0);
+            }
+            __syncwarp();
+            if (++as == AS) { as = 0; aph ^= 1; }
+            if (p.b_resident && tile != (int)blockIdx.x) continue;   // weights already resident in the ring
+            for (int dy = 0; dy < 3; ++dy) {
+              mbar_wait(&b_empty[bs], bph ^ 1);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(&b_full[bs], Cfg::B_BYTES);
+                tma_load_2d(smem_b + bs * Cfg::B_BYTES, &tmB, &b_full[bs], (dy * 3 + dx) * cin_pad + cb * BK, n_blk * BN);
               }
+              __syncwarp();
+              if (++bs == BS) { bs = 0; bph ^= 1; }
             }
           }
-          named_bar_sync(bar_id, 128);                         // slots are free (and residual loads in flight)
-          if (rd == 0) {
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tc_fence_after();
-          }
-          if (p.has_res_map && npan > 0) {
-            mbar_wait(&res_bar[half], res_phase);
-            res_phase ^= 1;
-          }
-          for (int s = 0; s < npan; ++s) {
-            uint8_t* srow = my_slots + s * PANEL_BYTES + r * 128;
-            const int pcol = (panel0 + 2 * s) * PW;            // first column of the panel inside the tile
-            const int nsub = PW / 32;
-#pragma unroll 1
-            for (int sub = 0; sub < nsub; ++sub) {
-              uint32_t v[32];
-              tmem_ld_32x32(t_row + pcol + sub * 32, v);
-              tmem_ld_wait();
-              float f[32];
-              const float4* b4 = reinterpret_cast<const float4*>(bs + pcol + sub * 32);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 bb = b4[q];
-                f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + bb.x;
-                f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb.y;
-                f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb.z;
-                f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb.w;
-              }
-              if (p.act != PGT_ACT_NONE) act_chunk(f, p.act);
-              if (esize == 2) {
-                // 32 bf16 = 64 B = chunks (sub*4 .. sub*4+3) of the 128 B swizzled row
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  uint4* dst = reinterpret_cast<uint4*>(srow + ((((sub << 2) + q) ^ (r & 7)) << 4));
-                  if (p.has_res_map) {
-                    const uint4 u = *dst;
-                    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-                    f[8 * q + 0] += a.x; f[8 * q + 1] += a.y; f[8 * q + 2] += b.x; f[8 * q + 3] += b.y;
-                    f[8 * q + 4] += c.x; f[8 * q + 5] += c.y; f[8 * q + 6] += d.x; f[8 * q + 7] += d.y;
-                  }
-                  uint4 o;
-                  o.x = pack_bf16x2(f[8 * q + 0], f[8 * q + 1]);
-                  o.y = pack_bf16x2(f[8 * q + 2], f[8 * q + 3]);
-                  o.z = pack_bf16x2(f[8 * q + 4], f[8 * q + 5]);
-                  o.w = pack_bf16x2(f[8 * q + 6], f[8 * q + 7]);
-                  *dst = o;
-                }
-              } else {
-                // 32 fp32 = 128 B = the whole swizzled row (nsub == 1)
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  float4* dst = reinterpret_cast<float4*>(srow + ((q ^ (r & 7)) << 4));
-                  float4 o = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-                  if (p.has_res_map) {
-                    const float4 u = *dst;
-                    o.x += u.x; o.y += u.y; o.z += u.z; o.w += u.w;
-                  }
-                  *dst = o;
-                }
-              }
-            }
-          }
-          fence_proxy_async();                                 // generic smem writes -> visible to the TMA engine
-          named_bar_sync(bar_id, 128);
-          if (leader) {
-            for (int s = 0; s < npan; ++s) {
-              const int c = col_base + (panel0 + 2 * s) * PW;
-              if (p.mode == MODE_LINEAR) tma_store_2d(&tmO, my_slots + s * PANEL_BYTES, c, m_blk * BM);
-              else tma_store_4d(&tmO, my_slots + s * PANEL_BYTES, c, x0, y0, n0);
-            }
-            bulk_commit();
-          }
-        }
-      } else {
-        // ---------------- direct path (SFT epilogue, NCHW fp32 output, unaligned views): per-thread global I/O
-        bool valid;
-        long long orow;
-        int pn = 0, py = 0, px = 0;
-        if (p.mode == MODE_LINEAR) {
-          orow = (long long)m_blk * BM + r;
-          valid = orow < p.M;
-        } else {
-          const int ix = r % p.tw;
-          const int t2 = r / p.tw;
-          const int iy = t2 % p.th;
-          const int in = t2 / p.th;
-          pn = n0 + in; py = y0 + iy; px = x0 + ix;
-          valid = (pn < p.F) && (py < p.H) && (px < p.W);
-          orow = ((long long)pn * p.H + py) * p.W + px;
-        }
-        mbar_wait(&tmem_full[acc], acc_phase);
-        tc_fence_after();
-        const int c_lo = half * (BN / 2), c_hi = c_lo + BN / 2;
-#pragma unroll 1
-        for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
-          if (col_base + c0 >= p.N) break;       // warp-uniform
-          uint32_t v[32];
-          tmem_ld_32x32(t_row + c0, v);
-          tmem_ld_wait();
-          if (valid) {
-            const int col0 = col_base + c0;
-            const int ncol = min(32, p.N - col0);
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bs[c0 + j];
-            if (p.act != PGT_ACT_NONE) act_chunk(f, p.act);
-            if (p.residual != nullptr) {
-              if (p.res_dtype == PGT_BF16) {
-                const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + orow * p.ldr + col0;
-                float rr[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) rr[j] = (j < ncol) ? __bfloat162float(rp[j]) : 0.f;
-                if (p.epi_mode == PGT_EPI_SFT) {
-                  const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(p.aux) + orow * p.ldaux + col0;
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) {
-                    const float sc = (j < ncol) ? __bfloat162float(ap[j]) : 0.f;
-                    f[j] = rr[j] + p.sft_w * (rr[j] * sc + f[j]);
-                  }
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) f[j] += rr[j];
-                }
-              } else {
-                const float* rp = reinterpret_cast<const float*>(p.residual) + orow * p.ldr + col0;
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < ncol) f[j] += __ldg(rp + j);
-              }
-            }
-            if (p.out_layout == PGT_OUT_NCHW) {
-              float* op = reinterpret_cast<float*>(p.out);
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncol) op[(((long long)pn * p.N + (col0 + j)) * p.H + py) * p.W + px] = f[j];
-            } else if (p.out_dtype == PGT_BF16) {
-              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col0;
-              if (ncol == 32 && ((p.ldo & 7) == 0)) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  uint4 u;
-                  u.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
-                  u.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
-                  u.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
-                  u.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
-                  reinterpret_cast<uint4*>(op)[q] = u;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < ncol) op[j] = __float2bfloat16_rn(f[j]);
-              }
-            } else {
-              float* op = reinterpret_cast<float*>(p.out) + orow * p.ldo + col0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncol) op[j] = f[j];
-            }
-          }
-          __syncwarp();
         }
       }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
     }
-    if (p.fast_epi && leader) bulk_wait0();      // all output bytes written before the CTA retires
+  } else if (warp == 1) {
+    {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        uint32_t accumulate = 0;
+        const int macros = 3 * p.cin_blocks;
+        for (int mc = 0; mc < macros; ++mc) {
+          mbar_wait(&a_full[as], aph);
+          const uint32_t a_addr = smem_u32(smem_a + as * HALO_A_BYTES);
+          for (int dy = 0; dy < 3; ++dy) {
+            if (!p.b_resident || it == 0) mbar_wait(&b_full[bs], bph);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t da = umma_desc_k_sw128(a_addr + dy * (HALO_TW * 128));
+              const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + bs * Cfg::B_BYTES));
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (accumulate | k) != 0 ? 1u : 0u);
+              if (!p.b_resident) umma_commit(&b_empty[bs]);
+              if (dy == 2) umma_commit(&a_empty[as]);
+              if (dy == 2 && mc == macros - 1) umma_commit(&tmem_full[acc]);
+            }
+            __syncwarp();
+            accumulate = 1;
+            if (++bs == BS) { bs = 0; bph ^= 1; }
+          }
+          if (++as == AS) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else {
+    EpiCtx ctx{staging, bias_s, tmem_full, tmem_empty, res_bar, tmem_base};
+    epilogue_loop<BN>(p, ctx, tmO, tmR, tmX, warp, lane, num_tiles);
   }
 
   tc_fence_before();
@@ -499,33 +739,28 @@ static int encode_out_map(CUtensorMap* map, const GemmParams& p, const void* bas
   }
   uint64_t dims[4] = {(uint64_t)p.N, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.F};
   uint64_t str[3] = {(uint64_t)ld * esize, (uint64_t)p.W * ld * esize, (uint64_t)p.H * p.W * ld * esize};
+  if (p.o_sx != 0 && base == p.out) {              // strided placement (only the output map, never the residual)
+    str[0] = (uint64_t)p.o_sx * esize; str[1] = (uint64_t)p.o_sy * esize; str[2] = (uint64_t)p.o_sf * esize;
+  }
   uint32_t box[4] = {pw, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
   return encode_map(map, base, 4, dims, str, box, dtype);
 }
 
-template <int BN>
-static int launch_gemm(const CUtensorMap& tmA, const void* W, int ldw, GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  static_assert(Cfg::STAGES >= 3, "pipeline too shallow");
-  CUtensorMap tmB, tmO, tmR;
-  {
-    // rows beyond N (weight matrices are not padded to BN rows) are zero-filled by TMA
-    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
-    uint64_t str[1] = {(uint64_t)ldw * 2};
-    uint32_t box[2] = {BK, (uint32_t)BN};
-    int rc = encode_map(&tmB, W, 2, dims, str, box);
-    if (rc != PGT_OK) return rc;
-  }
+static int setup_epilogue_maps(GemmParams& p, const CUtensorMap& placeholder, CUtensorMap& tmO, CUtensorMap& tmR,
+                               CUtensorMap& tmX) {
   const int esize = p.out_dtype == PGT_BF16 ? 2 : 4;
-  p.fast_epi = (p.out_layout == PGT_OUT_NHWC && p.epi_mode == PGT_EPI_PLAIN && aligned16(p.out) &&
-                ((long long)p.ldo * esize) % 16 == 0) ? 1 : 0;
+  p.fast_epi = (p.out_layout == PGT_OUT_NHWC && aligned16(p.out) && ((long long)p.ldo * esize) % 16 == 0) ? 1 : 0;
+  if (p.epi_mode == PGT_EPI_SFT &&
+      !(p.out_dtype == PGT_BF16 && aligned16(p.aux) && ((long long)p.ldaux * 2) % 16 == 0 && p.o_sx == 0))
+    p.fast_epi = 0;
   p.has_res_map = 0;
   if (p.fast_epi && p.residual != nullptr) {
     if (p.res_dtype == p.out_dtype && aligned16(p.residual) && ((long long)p.ldr * esize) % 16 == 0) p.has_res_map = 1;
     else p.fast_epi = 0;
   }
-  tmO = tmA;
-  tmR = tmA;                                       // placeholders when unused (never dereferenced)
+  tmO = placeholder;
+  tmR = placeholder;                               // placeholders when unused (never dereferenced)
+  tmX = placeholder;
   if (p.fast_epi) {
     int rc = encode_out_map(&tmO, p, p.out, p.ldo, p.out_dtype);
     if (rc != PGT_OK) return rc;
@@ -533,7 +768,32 @@ static int launch_gemm(const CUtensorMap& tmA, const void* W, int ldw, GemmParam
       rc = encode_out_map(&tmR, p, p.residual, p.ldr, p.res_dtype);
       if (rc != PGT_OK) return rc;
     }
+    if (p.epi_mode == PGT_EPI_SFT) {
+      if (!p.has_res_map) { p.fast_epi = 0; return PGT_OK; }
+      rc = encode_out_map(&tmX, p, p.aux, p.ldaux, PGT_BF16);
+      if (rc != PGT_OK) return rc;
+    }
   }
+  return PGT_OK;
+}
+
+static int encode_weight_map(CUtensorMap* tmB, const void* W, int ldw, int K, int N, int BN) {
+  // rows beyond N (weight matrices are not padded to BN rows) are zero-filled by TMA
+  uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+  uint64_t str[1] = {(uint64_t)ldw * 2};
+  uint32_t box[2] = {BK, (uint32_t)BN};
+  return encode_map(tmB, W, 2, dims, str, box);
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const void* W, int ldw, GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static_assert(Cfg::STAGES >= 3, "pipeline too shallow");
+  CUtensorMap tmB, tmO, tmR, tmX;
+  int rc = encode_weight_map(&tmB, W, ldw, p.K, p.N, BN);
+  if (rc != PGT_OK) return rc;
+  rc = setup_epilogue_maps(p, tmA, tmO, tmR, tmX);
+  if (rc != PGT_OK) return rc;
   p.n_tiles = ceil_div(p.N, BN);
   static bool attr_set = false;
   if (!attr_set) {
@@ -549,7 +809,35 @@ static int launch_gemm(const CUtensorMap& tmA, const void* W, int ldw, GemmParam
       else snprintf(desc, sizeof(desc), "conv%d s%d F%d H%d W%d K%d N%d BN%d t%dx%dx%d e%d", p.ksize, p.mode, p.F, p.H, p.W, p.K, p.N, BN, p.tn, p.th, p.tw, p.fast_epi);
     }
     ProfScope ps(PGT_PROF_GEMM, p.flops, stream, desc);
-    gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, tmR, p);
+    gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, tmR, tmX, p);
+  }
+  PGT_LAUNCH_OK();
+  return PGT_OK;
+}
+
+template <int BN>
+static int launch_halo(const CUtensorMap& tmA, const void* W, int ldw, GemmParams& p, cudaStream_t stream) {
+  using Cfg = HaloCfg<BN>;
+  CUtensorMap tmB, tmO, tmR, tmX;
+  int rc = encode_weight_map(&tmB, W, ldw, p.K, p.N, BN);
+  if (rc != PGT_OK) return rc;
+  rc = setup_epilogue_maps(p, tmA, tmO, tmR, tmX);
+  if (rc != PGT_OK) return rc;
+  p.n_tiles = ceil_div(p.N, BN);
+  p.b_resident = (9 * p.cin_blocks == Cfg::B_STAGES && p.n_tiles == 1) ? 1 : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PGT_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  {
+    char desc[96];
+    if (prof_enabled())
+      snprintf(desc, sizeof(desc), "halo3 F%d H%d W%d K%d N%d BN%d e%d r%d", p.F, p.H, p.W, p.K, p.N, BN, p.fast_epi, p.b_resident);
+    ProfScope ps(PGT_PROF_GEMM, p.flops, stream, desc);
+    conv_halo_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, tmR, tmX, p);
   }
   PGT_LAUNCH_OK();
   return PGT_OK;
@@ -617,10 +905,14 @@ extern "C" int pgt_linear_bf16(const void* A, int lda, const void* W, int ldw, i
   return dispatch_gemm(tmA, W, ldw, p, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int pgt_conv_bf16(const void* x, int F, int Hin, int Win, int Cin, int ldx, const void* Wp, int ldw,
-                             int Cout, int ksize, int stride, int pad_lo, const pgt_epilogue* ep, void* stream) {
+// pad_y/pad_x: zero rows/cols before the input (stride 1); up_phase >= 0: phase (py = up_phase>>1, px = up_phase&1)
+// of a nearest-x2-upsample-folded conv — the [F,Hin,Win,Cout] result is scattered to out[F, 2y+py, 2x+px, :].
+static int conv_impl(const void* x, int F, int Hin, int Win, int Cin, int ldx, const void* Wp, int ldw, int Cout,
+                     int ksize, int stride, int pad_y, int pad_x, int up_phase, const pgt_epilogue* ep, void* stream) {
+  const int pad_lo = pad_y;
   PGT_CHECK_ARG(x && Wp && F > 0 && Hin > 0 && Win > 0 && Cin > 0 && Cout > 0);
-  PGT_CHECK_ARG((ksize == 1 || ksize == 3) && (stride == 1 || stride == 2) && pad_lo >= 0 && pad_lo <= 1);
+  PGT_CHECK_ARG((ksize >= 1 && ksize <= 3) && (stride == 1 || stride == 2) && pad_y >= 0 && pad_y <= 1 && pad_x >= 0 && pad_x <= 1);
+  PGT_CHECK_ARG(stride == 1 || (ksize != 2 && pad_x == pad_y));
   PGT_CHECK_ARG((ldx % 8) == 0 && (ldw % 8) == 0 && aligned16(x) && aligned16(Wp) && ldx >= Cin);
   const int cin_pad = ceil_div(Cin, BK) * BK;
   PGT_CHECK_ARG(ldw >= ksize * ksize * cin_pad);
@@ -628,6 +920,7 @@ extern "C" int pgt_conv_bf16(const void* x, int F, int Hin, int Win, int Cin, in
   p.N = Cout;
   p.ksize = ksize;
   p.pad_lo = pad_lo;
+  p.pad_x = pad_x; p.pad_y = pad_y;
   p.cin_blocks = cin_pad / BK;
   p.K = ksize * ksize * cin_pad;
   p.num_kb = ksize * ksize * p.cin_blocks;
@@ -645,12 +938,27 @@ extern "C" int pgt_conv_bf16(const void* x, int F, int Hin, int Win, int Cin, in
   }
   rc = fill_epilogue(p, ep);
   if (rc != PGT_OK) return rc;
+  if (up_phase >= 0) {
+    if (stride != 1 || p.out_layout != PGT_OUT_NHWC || p.epi_mode != PGT_EPI_PLAIN || p.residual != nullptr)
+      return PGT_ERR_UNSUPPORTED;
+    const int py = up_phase >> 1, px = up_phase & 1;
+    const int esz = p.out_dtype == PGT_BF16 ? 2 : 4;
+    const long long Wo = 2LL * Win;
+    p.out = static_cast<char*>(p.out) + ((long long)py * Wo + px) * p.ldo * esz;
+    p.o_sx = 2LL * p.ldo; p.o_sy = 2LL * Wo * p.ldo; p.o_sf = 4LL * Hin * Win * p.ldo;
+  }
   // 128-pixel tile = tn frames x th rows x tw columns
-  int tw = 1;
-  while (tw * 2 <= p.W && tw * 2 <= BM) tw *= 2;
-  int th = 1;
-  while (th * 2 <= p.H && tw * th * 2 <= BM) th *= 2;
-  int tn = BM / (tw * th);
+  static const bool no_halo = getenv("PGT_NO_HALO") != nullptr;
+  const bool halo = !no_halo && up_phase < 0 && stride == 1 && ksize == 3 && pad_y == 1 && pad_x == 1 && Cout <= 128 && Hin >= HALO_TH &&
+                    Win >= HALO_TW;
+  int tw = 1, th = 1, tn;
+  if (halo) {
+    tw = HALO_TW; th = HALO_TH;
+  } else {
+    while (tw * 2 <= p.W && tw * 2 <= BM) tw *= 2;
+    while (th * 2 <= p.H && tw * th * 2 <= BM) th *= 2;
+  }
+  tn = BM / (tw * th);
   p.tw = tw; p.th = th; p.tn = tn;
   p.tiles_x = ceil_div(p.W, tw);
   p.tiles_y = ceil_div(p.H, th);
@@ -660,8 +968,12 @@ extern "C" int pgt_conv_bf16(const void* x, int F, int Hin, int Win, int Cin, in
   if (p.mode == MODE_CONV_S1) {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)F};
     uint64_t str[3] = {(uint64_t)ldx * 2, (uint64_t)Win * ldx * 2, (uint64_t)Hin * Win * ldx * 2};
-    uint32_t box[4] = {BK, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
+    uint32_t box[4] = {BK, (uint32_t)tw, (uint32_t)(halo ? th + 2 : th), (uint32_t)tn};
     rc = encode_map(&tmA, x, 4, dims, str, box);
+    if (rc == PGT_OK && halo) {
+      cudaStream_t st = static_cast<cudaStream_t>(stream);
+      return Cout <= 64 ? launch_halo<64>(tmA, Wp, ldw, p, st) : launch_halo<128>(tmA, Wp, ldw, p, st);
+    }
   } else {
     uint64_t dims[5] = {(uint64_t)2 * ldx, (uint64_t)Win / 2, 2, (uint64_t)Hin / 2, (uint64_t)F};
     uint64_t str[4] = {(uint64_t)2 * ldx * 2, (uint64_t)Win * ldx * 2, (uint64_t)2 * Win * ldx * 2,
@@ -670,5 +982,30 @@ extern "C" int pgt_conv_bf16(const void* x, int F, int Hin, int Win, int Cin, in
     rc = encode_map(&tmA, x, 5, dims, str, box);
   }
   if (rc != PGT_OK) return rc;
+  if (up_phase >= 0) {
+    // strided placement exists only on the TMA-store path
+    const int esz = p.out_dtype == PGT_BF16 ? 2 : 4;
+    if (!aligned16(p.out) || ((long long)p.ldo * esz) % 16 != 0) return PGT_ERR_UNSUPPORTED;
+  }
   return dispatch_gemm(tmA, Wp, ldw, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pgt_conv_bf16(const void* x, int F, int Hin, int Win, int Cin, int ldx, const void* Wp, int ldw,
+                             int Cout, int ksize, int stride, int pad_lo, const pgt_epilogue* ep, void* stream) {
+  PGT_CHECK_ARG(ksize == 1 || ksize == 3);
+  return conv_impl(x, F, Hin, Win, Cin, ldx, Wp, ldw, Cout, ksize, stride, pad_lo, pad_lo, -1, ep, stream);
+}
+
+extern "C" int pgt_conv_up2x_bf16(const void* x, int F, int Hin, int Win, int Cin, int ldx, const void* Wp4, int ldw,
+                                  int Cout, const pgt_epilogue* ep, void* stream) {
+  PGT_CHECK_ARG(Wp4 != nullptr && ldw > 0);
+  const int cin_pad = ceil_div(Cin, BK) * BK;
+  PGT_CHECK_ARG(ldw >= 4 * cin_pad);
+  for (int ph = 0; ph < 4; ++ph) {
+    const int py = ph >> 1, px = ph & 1;
+    const void* w = static_cast<const char*>(Wp4) + (size_t)ph * Cout * ldw * 2;
+    int rc = conv_impl(x, F, Hin, Win, Cin, ldx, w, ldw, Cout, 2, 1, 1 - py, 1 - px, ph, ep, stream);
+    if (rc != PGT_OK) return rc;
+  }
+  return PGT_OK;
 }

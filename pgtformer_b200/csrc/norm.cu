@@ -22,11 +22,12 @@ __device__ __forceinline__ void store8_bf16(__nv_bfloat16* p, const float (&v)[8
 
 // ---------------------------------------------------------------------------------- GroupNorm
 // Pass 1: per (frame, pixel-chunk) partial (sum, sumsq) of every group.  Thread (prow, vcol) owns 8 fixed
-// channels and strides over the chunk's pixels; channel sums are folded to groups at the end.
+// channels and strides over the chunk's pixels with 4 independent 16-byte loads in flight; the per-thread sums
+// are folded over prow through shared memory in a fixed order (deterministic), then channels -> groups.
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int HW, int C, int pix_per_chunk,
                 float* __restrict__ partial /*[F][chunks][32][2]*/) {
-  extern __shared__ float sm[];              // [2][C] channel sums, then reused
+  extern __shared__ float sm[];              // [rows_par][2][C] per-thread sums, reduced in place
   const int vc = C >> 3;
   const int rows_par = GN_THREADS / vc;
   const int vcol = threadIdx.x % vc;
@@ -39,46 +40,57 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int HW, int C, int
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
   if (prow < rows_par) {
     const __nv_bfloat16* base = x + ((size_t)f * HW) * ldx + vcol * 8;
-    for (int p = p0 + prow; p < p1; p += rows_par) {
+    int p = p0 + prow;
+    for (; p + 3 * rows_par < p1; p += 4 * rows_par) {
+      float v0[8], v1[8], v2[8], v3[8];
+      load8_bf16(base + (size_t)p * ldx, v0);
+      load8_bf16(base + (size_t)(p + rows_par) * ldx, v1);
+      load8_bf16(base + (size_t)(p + 2 * rows_par) * ldx, v2);
+      load8_bf16(base + (size_t)(p + 3 * rows_par) * ldx, v3);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += (v0[i] + v1[i]) + (v2[i] + v3[i]);
+        q[i] += (v0[i] * v0[i] + v1[i] * v1[i]) + (v2[i] * v2[i] + v3[i] * v3[i]);
+      }
+    }
+    for (; p < p1; p += rows_par) {
       float v[8];
       load8_bf16(base + (size_t)p * ldx, v);
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] += v[i] * v[i]; }
     }
-  }
-  for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) sm[i] = 0.f;
-  __syncthreads();
-  // serialised accumulation over prow keeps the order fixed (deterministic)
-  for (int rr = 0; rr < rows_par; ++rr) {
-    if (prow == rr) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        sm[vcol * 8 + i] += s[i];
-        sm[C + vcol * 8 + i] += q[i];
-      }
+    for (int i = 0; i < 8; ++i) {
+      sm[(prow * 2 + 0) * C + vcol * 8 + i] = s[i];
+      sm[(prow * 2 + 1) * C + vcol * 8 + i] = q[i];
     }
-    __syncthreads();
   }
+  __syncthreads();
+  // channel totals: thread c sums its column over prow in a fixed order
+  for (int c = threadIdx.x; c < 2 * C; c += GN_THREADS) {
+    const int which = c / C, ch = c % C;
+    float t = 0.f;
+    for (int rr = 0; rr < rows_par; ++rr) t += sm[(rr * 2 + which) * C + ch];
+    sm[(size_t)rows_par * 2 * C + c] = t;
+  }
+  __syncthreads();
   if (threadIdx.x < GN_GROUPS) {
+    const float* tot = sm + (size_t)rows_par * 2 * C;
     const int cpg = C / GN_GROUPS;
     float gs = 0.f, gq = 0.f;
-    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) { gs += sm[c]; gq += sm[C + c]; }
+    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) { gs += tot[c]; gq += tot[C + c]; }
     float* o = partial + (((size_t)f * nchunks + chunk) * GN_GROUPS + threadIdx.x) * 2;
     o[0] = gs; o[1] = gq;
   }
 }
 
-// Pass 2: y = act(x * a[c] + b[c]) with a = rstd*gamma, b = beta - mean*rstd*gamma.
+// Pass 2 (tiny): fold the chunk partials (fp64) into per-(frame, channel) affine terms
+// a = rstd*gamma, b = beta - mean*rstd*gamma, stored after the partials in the workspace.
 __global__ void __launch_bounds__(256)
-gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int HW, int C, int pix_per_block, int nchunks,
-                const float* __restrict__ partial, const float* __restrict__ gamma, const float* __restrict__ beta,
-                float eps, int apply_silu, __nv_bfloat16* __restrict__ y, int ldy) {
-  extern __shared__ float sm[];              // a[C], b[C], mean[32], rstd[32]
-  float* sa = sm;
-  float* sb = sm + C;
-  float* smean = sm + 2 * C;
-  float* srstd = smean + GN_GROUPS;
-  const int f = blockIdx.y;
+gn_finalize_kernel(const float* __restrict__ partial, int nchunks, int HW, int C, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float eps, float* __restrict__ ab /*[F][2][C]*/) {
+  __shared__ float smean[GN_GROUPS], srstd[GN_GROUPS];
+  const int f = blockIdx.x;
   const int cpg = C / GN_GROUPS;
   if (threadIdx.x < GN_GROUPS) {
     double s = 0.0, q = 0.0;
@@ -97,82 +109,130 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int HW, int C, int
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
     const float a = srstd[g] * gamma[c];
-    sa[c] = a;
-    sb[c] = beta[c] - smean[g] * a;
+    ab[((size_t)f * 2 + 0) * C + c] = a;
+    ab[((size_t)f * 2 + 1) * C + c] = beta[c] - smean[g] * a;
   }
-  __syncthreads();
+}
+
+// Pass 3: y = act(x * a[c] + b[c]); thread (prow, vcol) keeps its 8 channels' a/b in registers and strides over
+// pixels with two independent 16-byte loads in flight.
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int HW, int C, int pix_per_block,
+                const float* __restrict__ ab, int apply_silu, __nv_bfloat16* __restrict__ y, int ldy) {
+  const int f = blockIdx.y;
   const int vc = C >> 3;
+  const int rows_par = GN_THREADS / vc;
+  const int vcol = threadIdx.x % vc;
+  const int prow = threadIdx.x / vc;
+  if (prow >= rows_par) return;
+  float a[8], b[8];
+  {
+    const float4* pa = reinterpret_cast<const float4*>(ab + ((size_t)f * 2 + 0) * C + vcol * 8);
+    const float4* pb = reinterpret_cast<const float4*>(ab + ((size_t)f * 2 + 1) * C + vcol * 8);
+    const float4 a0 = __ldg(pa), a1 = __ldg(pa + 1), b0 = __ldg(pb), b1 = __ldg(pb + 1);
+    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+  }
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
-  const size_t total = (size_t)(p1 - p0) * vc;
-  for (size_t i = threadIdx.x; i < total; i += blockDim.x) {
-    const int p = p0 + (int)(i / vc);
-    const int c0 = (int)(i % vc) * 8;
-    float v[8];
-    load8_bf16(x + ((size_t)f * HW + p) * ldx + c0, v);
+  const __nv_bfloat16* xb = x + ((size_t)f * HW) * ldx + vcol * 8;
+  __nv_bfloat16* yb = y + ((size_t)f * HW) * ldy + vcol * 8;
+  auto act = [&](float (&v)[8]) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float t = v[j] * sa[c0 + j] + sb[c0 + j];
-      v[j] = apply_silu ? t / (1.0f + __expf(-t)) : t;
+      const float t = fmaf(v[j], a[j], b[j]);
+      v[j] = apply_silu ? t * __frcp_rn(1.0f + __expf(-t)) : t;
     }
-    store8_bf16(y + ((size_t)f * HW + p) * ldy + c0, v);
+  };
+  int p = p0 + prow;
+  for (; p + 3 * rows_par < p1; p += 4 * rows_par) {       // four independent 16-byte loads in flight per thread
+    float v0[8], v1[8], v2[8], v3[8];
+    load8_bf16(xb + (size_t)p * ldx, v0);
+    load8_bf16(xb + (size_t)(p + rows_par) * ldx, v1);
+    load8_bf16(xb + (size_t)(p + 2 * rows_par) * ldx, v2);
+    load8_bf16(xb + (size_t)(p + 3 * rows_par) * ldx, v3);
+    act(v0); act(v1); act(v2); act(v3);
+    store8_bf16(yb + (size_t)p * ldy, v0);
+    store8_bf16(yb + (size_t)(p + rows_par) * ldy, v1);
+    store8_bf16(yb + (size_t)(p + 2 * rows_par) * ldy, v2);
+    store8_bf16(yb + (size_t)(p + 3 * rows_par) * ldy, v3);
+  }
+  for (; p < p1; p += rows_par) {
+    float v[8];
+    load8_bf16(xb + (size_t)p * ldx, v);
+    act(v);
+    store8_bf16(yb + (size_t)p * ldy, v);
   }
 }
 
 // ---------------------------------------------------------------------------------- LayerNorm
-// One warp per token row; two-pass (mean, then centred variance) entirely in registers.
-template <int MAXV>   // max 8-element vectors per lane: C <= 256 * MAXV
+// One warp per token row, LN_ROWS rows per warp in flight (all loads issued before any reduction) so that
+// enough 16-byte requests are outstanding to approach HBM bandwidth; two-pass statistics in registers.
+constexpr int LN_ROWS = 4;
+template <int NV>   // 8-element vectors per lane: C == 256 * NV
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const void* __restrict__ xin, int ldx, int x_dtype, int T, int C, const float* __restrict__ gamma,
+layernorm_kernel(const void* __restrict__ xin, int ldx, int x_dtype, int T, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, int ldy,
                  const __nv_bfloat16* __restrict__ pos, int ldpos, __nv_bfloat16* __restrict__ y2, int ldy2) {
+  constexpr int C = 256 * NV;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= T) return;
-  const int nv = C >> 8;                       // vectors of 8 per lane (C multiple of 256)
-  float v[MAXV][8];
+  const int row0 = warp * LN_ROWS;
+  if (row0 >= T) return;
+  float v[LN_ROWS][NV][8];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    if (i < nv) {
+  for (int r = 0; r < LN_ROWS; ++r) {
+    const int row = min(row0 + r, T - 1);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
       const int c0 = (i * 32 + lane) * 8;
       if (x_dtype == PGT_BF16) {
-        load8_bf16(reinterpret_cast<const __nv_bfloat16*>(xin) + (size_t)warp * ldx + c0, v[i]);
+        load8_bf16(reinterpret_cast<const __nv_bfloat16*>(xin) + (size_t)row * ldx + c0, v[r][i]);
       } else {
-        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(xin) + (size_t)warp * ldx + c0);
+        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(xin) + (size_t)row * ldx + c0);
         const float4 a = __ldg(p), b = __ldg(p + 1);
-        v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
-        v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
+        v[r][i][0] = a.x; v[r][i][1] = a.y; v[r][i][2] = a.z; v[r][i][3] = a.w;
+        v[r][i][4] = b.x; v[r][i][5] = b.y; v[r][i][6] = b.z; v[r][i][7] = b.w;
       }
     }
   }
-  float s = 0.f;
+  float g[NV][8], bt[NV][8];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i)
-    if (i < nv)
+  for (int i = 0; i < NV; ++i) {
+    const int c0 = (i * 32 + lane) * 8;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += v[i][j];
-  const float mean = warp_sum(s) / (float)C;
-  float q = 0.f;
+    for (int j = 0; j < 8; ++j) { g[i][j] = __ldg(gamma + c0 + j); bt[i][j] = __ldg(beta + c0 + j); }
+  }
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i)
-    if (i < nv)
+  for (int r = 0; r < LN_ROWS; ++r) {
+    const int row = row0 + r;
+    float s = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
-  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    for (int i = 0; i < NV; ++i)
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    if (i < nv) {
-      const int c0 = (i * 32 + lane) * 8;
-      float o[8];
+      for (int j = 0; j < 8; ++j) s += v[r][i][j];
+    const float mean = warp_sum(s) * (1.0f / C);
+    float q = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * __ldg(gamma + c0 + j) + __ldg(beta + c0 + j);
-      store8_bf16(y + (size_t)warp * ldy + c0, o);
-      if (y2 != nullptr) {
-        float pv[8];
-        load8_bf16(pos + (size_t)warp * ldpos + c0, pv);
+    for (int i = 0; i < NV; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] += pv[j];
-        store8_bf16(y2 + (size_t)warp * ldy2 + c0, o);
+      for (int j = 0; j < 8; ++j) { const float d = v[r][i][j] - mean; q += d * d; }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
+    if (row < T) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c0 = (i * 32 + lane) * 8;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[r][i][j] - mean) * rstd * g[i][j] + bt[i][j];
+        store8_bf16(y + (size_t)row * ldy + c0, o);
+        if (y2 != nullptr) {
+          float pv[8];
+          load8_bf16(pos + (size_t)row * ldpos + c0, pv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += pv[j];
+          store8_bf16(y2 + (size_t)row * ldy2 + c0, o);
+        }
       }
     }
   }
@@ -257,8 +317,7 @@ static int gn_chunks(int HW) {
 }
 
 extern "C" int64_t pgt_groupnorm_ws_floats(int F, int HW, int C) {
-  (void)C;
-  return (int64_t)F * gn_chunks(HW) * GN_GROUPS * 2;
+  return (int64_t)F * gn_chunks(HW) * GN_GROUPS * 2 + (int64_t)F * 2 * C;
 }
 
 extern "C" int pgt_groupnorm_silu(const void* x, int ldx, int F, int HW, int C, const float* gamma, const float* beta,
@@ -269,15 +328,19 @@ extern "C" int pgt_groupnorm_silu(const void* x, int ldx, int F, int HW, int C, 
   ProfScope ps(PGT_PROF_NORM, 3.0 * F * (double)HW * C * 2, st);     // read, read, write (bf16)
   const int nchunks = gn_chunks(HW);
   const int ppc = ceil_div(HW, nchunks);
-  gn_stats_kernel<<<dim3(nchunks, F), GN_THREADS, 2 * C * sizeof(float), st>>>(
+  float* ab = ws + (size_t)F * nchunks * GN_GROUPS * 2;
+  const size_t stats_smem = ((size_t)(GN_THREADS / (C / 8)) + 1) * 2 * C * sizeof(float);   // <= 2*(512*8+C)*4 B
+  gn_stats_kernel<<<dim3(nchunks, F), GN_THREADS, stats_smem, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C, ppc, ws);
   PGT_LAUNCH_OK();
-  // apply: ~16 KB of activations per block
-  int ppb = (16384 / (C * 2));
-  if (ppb < 8) ppb = 8;
+  gn_finalize_kernel<<<F, 256, 0, st>>>(ws, nchunks, HW, C, gamma, beta, eps, ab);
+  PGT_LAUNCH_OK();
+  // apply: ~128 KB of activations per block
+  int ppb = (131072 / (C * 2));
+  if (ppb < 16) ppb = 16;
   const int nblk = ceil_div(HW, ppb);
-  gn_apply_kernel<<<dim3(nblk, F), 256, (2 * C + 2 * GN_GROUPS) * sizeof(float), st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C, ppb, nchunks, ws, gamma, beta, eps, apply_silu,
+  gn_apply_kernel<<<dim3(nblk, F), GN_THREADS, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C, ppb, ab, apply_silu,
       reinterpret_cast<__nv_bfloat16*>(y), ldy);
   PGT_LAUNCH_OK();
   return PGT_OK;
@@ -290,11 +353,16 @@ extern "C" int pgt_layernorm(const void* x, int ldx, int x_dtype, int T, int C, 
   PGT_CHECK_ARG(C % 256 == 0 && C <= 1024 && ldx % 8 == 0 && ldy % 8 == 0);
   PGT_CHECK_ARG(y2 == nullptr || (pos != nullptr && ldpos % 8 == 0 && ldy2 % 8 == 0));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope ps(7, (double)T * C * ((x_dtype == PGT_BF16 ? 2.0 : 4.0) + 2.0 + (y2 ? 4.0 : 0.0)), st, "layernorm");
   const int warps_per_block = 8;
-  const int grid = ceil_div(T, warps_per_block);
-  layernorm_kernel<4><<<grid, warps_per_block * 32, 0, st>>>(
-      x, ldx, x_dtype, T, C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y), ldy,
-      reinterpret_cast<const __nv_bfloat16*>(pos), ldpos, reinterpret_cast<__nv_bfloat16*>(y2), ldy2);
+  const int grid = ceil_div(T, warps_per_block * LN_ROWS);
+  auto yb = reinterpret_cast<__nv_bfloat16*>(y);
+  auto pb = reinterpret_cast<const __nv_bfloat16*>(pos);
+  auto y2b = reinterpret_cast<__nv_bfloat16*>(y2);
+  if (C == 256) layernorm_kernel<1><<<grid, 256, 0, st>>>(x, ldx, x_dtype, T, gamma, beta, eps, yb, ldy, pb, ldpos, y2b, ldy2);
+  else if (C == 512) layernorm_kernel<2><<<grid, 256, 0, st>>>(x, ldx, x_dtype, T, gamma, beta, eps, yb, ldy, pb, ldpos, y2b, ldy2);
+  else if (C == 768) layernorm_kernel<3><<<grid, 256, 0, st>>>(x, ldx, x_dtype, T, gamma, beta, eps, yb, ldy, pb, ldpos, y2b, ldy2);
+  else layernorm_kernel<4><<<grid, 256, 0, st>>>(x, ldx, x_dtype, T, gamma, beta, eps, yb, ldy, pb, ldpos, y2b, ldy2);
   PGT_LAUNCH_OK();
   return PGT_OK;
 }
@@ -302,6 +370,7 @@ extern "C" int pgt_layernorm(const void* x, int ldx, int x_dtype, int T, int C, 
 extern "C" int pgt_adain(const void* q, int ldq, int q_dtype, const void* l, int ldl, int F, int HW, int C, float eps,
                          void* y, int ldy, void* stream) {
   PGT_CHECK_ARG(q && l && y && F > 0 && HW > 1 && C % 64 == 0 && ldq % 8 == 0 && ldl % 8 == 0 && ldy % 8 == 0);
+  ProfScope ps(PGT_PROF_MOVE, 8.0 * F * (double)HW * C, static_cast<cudaStream_t>(stream), "adain");
   adain_kernel<<<dim3(C / 64, F), ADAIN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       q, ldq, q_dtype, reinterpret_cast<const __nv_bfloat16*>(l), ldl, HW, C, eps,
       reinterpret_cast<__nv_bfloat16*>(y), ldy);

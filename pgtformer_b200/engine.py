@@ -30,6 +30,25 @@ def _pack_conv(w):
     return wp.reshape(co, kh * kw * cp).to(BF).contiguous()
 
 
+def _pack_up2x(w):
+    """OIHW 3x3 fp32 -> [4, Cout, 4*CinPad] bf16 phase weights of the upsample-folded conv (include/pgt_b200.h):
+    phase (py,px), tap (ty,tx) = sum of w[dy,dx] over dy in S(py,ty), dx in S(px,tx); sums in fp32, one bf16 rounding."""
+    co, ci, _, _ = w.shape
+    cp = (ci + 63) // 64 * 64
+    sets = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}
+    out = torch.zeros(4, co, 4, cp, dtype=torch.float32, device=w.device)
+    for py in range(2):
+        for px in range(2):
+            for ty in range(2):
+                for tx in range(2):
+                    acc = torch.zeros(co, ci, dtype=torch.float32, device=w.device)
+                    for dy in sets[py][ty]:
+                        for dx in sets[px][tx]:
+                            acc += w[:, :, dy, dx]
+                    out[py * 2 + px, :, ty * 2 + tx, :ci] = acc
+    return out.reshape(4, co, 4 * cp).to(BF).contiguous()
+
+
 def _pack_lin(w):
     """[N, K] (or [N, K, 1, 1]) fp32 -> [N, roundup(K, 8)] bf16."""
     w = w.reshape(w.shape[0], -1)
@@ -63,6 +82,8 @@ class Engine:
             if name.endswith('.weight') and t.dim() == 4:
                 if name == 'encoder.conv_in.weight':
                     w[name] = t.float().contiguous()
+                elif t.shape[2] == 3 and '.upsample.conv.' in name:
+                    w[name] = _pack_up2x(t.float())
                 elif t.shape[2] == 3:
                     w[name] = _pack_conv(t.float())
                 else:
@@ -237,8 +258,8 @@ class Engine:
                 h = self.fuse_sft(feats[lvl], h, a.fuse_level_key[lvl], wgt)
             if lvl != 0:
                 Fr, H, W, C = h.shape
-                up = ops.upsample2x(h, self._new(Fr, 2 * H, 2 * W, C))
-                h = self._conv3(up, 'decoder.up.%d.upsample.conv' % lvl, C)
+                p = 'decoder.up.%d.upsample.conv' % lvl
+                h = ops.conv_up2x(h, self.w[p + '.weight'], C, self._new(Fr, 2 * H, 2 * W, C), bias=self.w[p + '.bias'])
         Fr, H, W, _ = h.shape
         out = self._new(Fr, a.out_ch, H, W, dtype=torch.float32)
         self._conv3(self._gn(h, 'decoder.norm_out'), 'decoder.conv_out', a.out_ch, out=out, nchw=True)
@@ -249,7 +270,9 @@ class Engine:
         (`archs/pgtformer_arch.py:606-614`)."""
         Fr, _, H, W = x.shape
         hh, ww = H // 16, W // 16
-        cond = self._bisenet((x - self.img_mean) / self.img_std)
+        with torch.autocast('cuda', dtype=BF):           # cuDNN bf16 tensor-core path for the parsing net (round 1)
+            cond = self._bisenet(((x - self.img_mean) / self.img_std).contiguous(memory_format=torch.channels_last))
+        cond = cond.float()
         cond_nhwc = torch.zeros(Fr, hh, ww, 64, dtype=BF, device=self.dev)
         ops.nchw_to_nhwc(cond.contiguous(), cond_nhwc)
         return self._lin(cond_nhwc.view(Fr * hh * ww, 64), 'convpos', 512, K=57)

@@ -94,6 +94,18 @@ def conv(x, wp, cout, out, ksize=3, stride=1, pad_lo=1, bias=None, act=ACT_NONE,
     return out
 
 
+def conv_up2x(x, wp4, cout, out, bias=None, act=ACT_NONE):
+    """nearest x2 upsample + conv3x3 folded into four 2x2 phase convs; wp4 [4, cout, 4*CinPad] bf16."""
+    lib = L.load()
+    F, H, W, Cin = x.shape
+    assert x.dtype == torch.bfloat16 and wp4.dtype == torch.bfloat16 and wp4.is_contiguous() and wp4.dim() == 3
+    assert tuple(out.shape) == (F, 2 * H, 2 * W, cout) and out.is_contiguous()
+    ep = make_epilogue(out, bias, act)
+    L.check(lib.pgt_conv_up2x_bf16(_p(x), F, H, W, Cin, x.stride(2), _p(wp4), wp4.stride(1), cout, ctypes.byref(ep),
+                                   _stream()))
+    return out
+
+
 def conv_in_rgb(x_nchw, w, bias, out):
     lib = L.load()
     F, C, H, W = x_nchw.shape
@@ -220,7 +232,7 @@ def reset_launch_count():
     L.load().pgt_reset_launch_count()
 
 
-PROF_CLASSES = ('gemm_tc', 'window_attn', 'mha', 'argmax_gather', 'l2_argmin', 'groupnorm', 'move', 'other')
+PROF_CLASSES = ('gemm_tc', 'window_attn', 'mha', 'argmax_gather', 'l2_argmin', 'groupnorm', 'move', 'layernorm')
 
 
 def profile_begin():

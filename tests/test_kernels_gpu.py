@@ -129,6 +129,8 @@ def conv_ref(x_nhwc, w, b, stride=1, pad=(1, 1, 1, 1)):
     (3, 16, 16, 288, 128),     # Cin = 4.5 x 64: channel tail zero-filled by TMA
     (2, 64, 64, 64, 96),
     (3, 4, 4, 64, 64),
+    (3, 24, 40, 64, 128),      # halo tiles (8x16) with ragged bottom / right edges
+    (1, 8, 16, 128, 32),
 ])
 def test_conv3x3(Fr, H, W, Cin, Cout):
     o = ops()
@@ -187,6 +189,23 @@ def test_conv1x1_stride2():
     out = torch.empty(Fr, H // 2, W // 2, Cout, dtype=torch.float32, device=DEV)
     o.conv(x.to(DEV), pack_conv_weight(w).to(DEV), Cout, out, ksize=1, stride=2, pad_lo=0)
     check_close(out, conv_ref(x, w, None, stride=2, pad=(0, 0, 0, 0)), 'conv1x1 s2')
+
+
+@pytest.mark.parametrize('Fr,H,W,C', [(3, 8, 8, 64), (3, 16, 16, 128), (2, 4, 4, 512), (3, 32, 32, 256)])
+def test_conv_up2x_folded(Fr, H, W, C):
+    """nearest x2 + conv3x3 (tdcrqvae3_arch.py:45-52) as four 2x2 phase convs on the source resolution."""
+    from pgtformer_b200.engine import _pack_up2x
+    o = ops()
+    x = bf(rnd((Fr, H, W, C), 35))
+    w = bf(rnd((C, C, 3, 3), 36, (9 * C) ** -0.5)).float()
+    b = rnd((C,), 37, 0.1)
+    out = torch.empty(Fr, 2 * H, 2 * W, C, dtype=torch.bfloat16, device=DEV)
+    o.conv_up2x(x.to(DEV), _pack_up2x(w.to(DEV)), C, out, bias=b.to(DEV))
+    torch.cuda.synchronize()
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode='nearest')
+    ref = F.conv2d(up, w, b, padding=1).permute(0, 2, 3, 1)
+    # tap-summed weights are rounded to bf16 once more: allow 2 ulp
+    check_close(out, ref, 'conv up2x', bf16_out=True, rel=6e-3)
 
 
 def test_conv_in_rgb():
