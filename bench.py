@@ -171,12 +171,12 @@ def main():
     x_host = torch.rand(b * 3, 3, H, H, generator=g).pin_memory()
     x_dev = x_host.to(dev)
     out_host = torch.empty(b * 3, 3, H, H, dtype=torch.float32).pin_memory()
-    gathered = torch.empty(world * b * 3, 3, H, H, dtype=torch.float32, device=dev) if world > 1 else None
+    from pgtformer_b200.parallel import gather_frames
 
     def step_resident():
         out = model(x_dev, w=1, adain=True)[0]
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out)      # the path's one collective
+            out = gather_frames(out, world * b)             # the path's one collective, NCCL
         return out
 
     def step_e2e():

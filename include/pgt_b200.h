@@ -38,6 +38,8 @@ enum { PGT_ACT_NONE = 0, PGT_ACT_GELU = 1, PGT_ACT_SILU = 2, PGT_ACT_LRELU02 = 3
 enum { PGT_EPI_PLAIN = 0,    /* y = act(acc + bias) [+ residual]                           */
        PGT_EPI_SFT = 1 };    /* y = r + w * (r * aux + (acc + bias)); r = residual         */
 enum { PGT_OUT_NHWC = 0, PGT_OUT_NCHW = 1 };
+/* act must be PGT_ACT_RELU: y = relu(acc + bias + residual)  (ResNet BasicBlock, archs/pgtformer_arch.py:56-68) */
+enum { PGT_EPI_FLAG_RELU_AFTER_RESIDUAL = 1 };
 
 /* Fused epilogue shared by the tensor-core GEMM / implicit-GEMM conv. */
 typedef struct pgt_epilogue {
@@ -54,7 +56,7 @@ typedef struct pgt_epilogue {
   int32_t ldo;
   int32_t out_dtype;     /* PGT_BF16 / PGT_F32                                             */
   int32_t out_layout;    /* PGT_OUT_NHWC / PGT_OUT_NCHW                                    */
-  int32_t reserved;
+  int32_t flags;         /* PGT_EPI_FLAG_*                                                  */
 } pgt_epilogue;
 
 const char* pgt_strerror(int status);
@@ -166,6 +168,23 @@ int pgt_l2_argmin(const float* z, int T, int E, const float* codebook, int K, in
  * Replaces adaptive_instance_normalization (archs/codeformer_arch.py:15-46). */
 int pgt_adain(const void* q, int ldq, int q_dtype, const void* l, int ldl, int F, int HW, int C, float eps,
               void* y, int ldy, void* stream);
+
+/* ---- face-parsing branch (BiSeNet / ResNet18, archs/pgtformer_arch.py:34-397); its other convolutions run on
+ * pgt_conv_bf16 / pgt_conv_up2x_bf16 / pgt_linear_bf16 with eval-mode BatchNorm folded into weights and bias.
+ * pgt_stem7x7_rgb: conv 7x7 s2 p3 (3->64, BN folded, fp32 OIHW weights) + ReLU on the ImageNet-normalised image
+ *   ((x-mean)/std fused into the load; mean/stdv are HOST pointers to 3 floats) -> bf16 [F,H/2,W/2,64]  (:91-94, :606)
+ * pgt_maxpool3x3s2: MaxPool2d(3, 2, 1) (:84,:94)        pgt_global_avgpool: F.avg_pool2d(x, x.size()[2:]) -> bf16 [F,C]
+ * pgt_channel_affine: y = x * (scale[f,c] (+1)) + addv[f,c] + addm — ARM / FFM re-weighting (:203, :236-245, :331-333)
+ * pgt_assemble_cond: bilinear(align_corners) resize of heads 0,1 to (h16,w16) + head 2, concatenated into the
+ *   64-wide (57 used) conditioning map (:375-379). */
+int pgt_stem7x7_rgb(const float* x_nchw, int F, int H, int W, const float* mean, const float* stdv, const float* w,
+                    const float* bias, void* y, int ldy, void* stream);
+int pgt_maxpool3x3s2(const void* x, int ldx, int F, int H, int W, int C, void* y, int ldy, void* stream);
+int pgt_global_avgpool(const void* x, int ldx, int F, int HW, int C, void* y, int ldy, void* stream);
+int pgt_channel_affine(const void* x, int ldx, int F, int HW, int C, const void* scale, int lds, int plus_one,
+                       const void* addv, int ldv, const void* addm, int ldm, void* y, int ldy, void* stream);
+int pgt_assemble_cond(const void* o0, int ld0, const void* o1, int ld1, const void* o2, int ld2, int F, int h8, int w8,
+                      int h16, int w16, int ncls, void* cond, int ldc, void* stream);
 
 /* ---- layout / elementwise helpers on NHWC bf16 */
 /* nearest x2 upsample [F,H,W,C] -> [F,2H,2W,C]  (F.interpolate in archs/tdcrqvae3_arch.py:48) */

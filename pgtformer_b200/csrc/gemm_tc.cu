@@ -54,6 +54,7 @@ struct GemmParams {
   int has_res_map;       // fast path: residual is TMA-loaded through tmR
   const float* bias;
   int act, epi_mode;
+  int relu_after_res;    // ResNet BasicBlock: out = relu(conv + shortcut) — ReLU applied after the residual add
   const void* residual;
   int ldr, res_dtype;
   const void* aux;
@@ -139,7 +140,7 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, c
     f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb.z;
     f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb.w;
   }
-  if (p.act != PGT_ACT_NONE) act_chunk(f, p.act);
+  if (p.act != PGT_ACT_NONE && !p.relu_after_res) act_chunk(f, p.act);
   if (esize == 2) {
     // 32 bf16 = 64 B = chunks (sub*4 .. sub*4+3) of the 128 B swizzled row
 #pragma unroll
@@ -161,6 +162,10 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, c
           for (int e = 0; e < 8; ++e) f[8 * q + e] += rr[e];
         }
       }
+      if (p.relu_after_res) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[8 * q + e] = fmaxf(f[8 * q + e], 0.f);
+      }
       uint4 o;
       o.x = pack_bf16x2(f[8 * q + 0], f[8 * q + 1]);
       o.y = pack_bf16x2(f[8 * q + 2], f[8 * q + 3]);
@@ -178,6 +183,7 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, c
         const float4 u = *dst;
         o.x += u.x; o.y += u.y; o.z += u.z; o.w += u.w;
       }
+      if (p.relu_after_res) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
       *dst = o;
     }
   }
@@ -331,7 +337,7 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, const EpiCtx&
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bs[c0 + j];
-          if (p.act != PGT_ACT_NONE) act_chunk(f, p.act);
+          if (p.act != PGT_ACT_NONE && !p.relu_after_res) act_chunk(f, p.act);
           if (p.residual != nullptr) {
             if (p.res_dtype == PGT_BF16) {
               const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + orow * p.ldr + col0;
@@ -356,6 +362,7 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, const EpiCtx&
                 if (j < ncol) f[j] += __ldg(rp + j);
             }
           }
+          if (p.relu_after_res) act_chunk(f, PGT_ACT_RELU);
           if (p.out_layout == PGT_OUT_NCHW) {
             float* op = reinterpret_cast<float*>(p.out);
 #pragma unroll
@@ -874,6 +881,8 @@ static int fill_epilogue(GemmParams& p, const pgt_epilogue* ep) {
   p.ldo = ep->ldo;
   p.out_dtype = ep->out_dtype;
   p.out_layout = ep->out_layout;
+  p.relu_after_res = (ep->flags & PGT_EPI_FLAG_RELU_AFTER_RESIDUAL) ? 1 : 0;
+  if (p.relu_after_res && (p.act != PGT_ACT_RELU || p.epi_mode != PGT_EPI_PLAIN)) return PGT_ERR_INVALID;
   if (p.epi_mode == PGT_EPI_SFT && (p.residual == nullptr || p.aux == nullptr || p.res_dtype != PGT_BF16))
     return PGT_ERR_INVALID;
   if (p.out_layout == PGT_OUT_NCHW && (p.out_dtype != PGT_F32 || p.mode == MODE_LINEAR)) return PGT_ERR_INVALID;

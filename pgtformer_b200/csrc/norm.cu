@@ -116,12 +116,13 @@ gn_finalize_kernel(const float* __restrict__ partial, int nchunks, int HW, int C
 
 // Pass 3: y = act(x * a[c] + b[c]); thread (prow, vcol) keeps its 8 channels' a/b in registers and strides over
 // pixels with two independent 16-byte loads in flight.
-__global__ void __launch_bounds__(GN_THREADS)
+constexpr int GN_APPLY_THREADS = 256;
+__global__ void __launch_bounds__(GN_APPLY_THREADS, 3)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int HW, int C, int pix_per_block,
                 const float* __restrict__ ab, int apply_silu, __nv_bfloat16* __restrict__ y, int ldy) {
   const int f = blockIdx.y;
   const int vc = C >> 3;
-  const int rows_par = GN_THREADS / vc;
+  const int rows_par = GN_APPLY_THREADS / vc;
   const int vcol = threadIdx.x % vc;
   const int prow = threadIdx.x / vc;
   if (prow >= rows_par) return;
@@ -323,7 +324,7 @@ extern "C" int64_t pgt_groupnorm_ws_floats(int F, int HW, int C) {
 extern "C" int pgt_groupnorm_silu(const void* x, int ldx, int F, int HW, int C, const float* gamma, const float* beta,
                                   float eps, int apply_silu, void* y, int ldy, float* ws, void* stream) {
   PGT_CHECK_ARG(x && y && ws && gamma && beta && F > 0 && HW > 0);
-  PGT_CHECK_ARG(C % 32 == 0 && C % 8 == 0 && C / 8 <= GN_THREADS && ldx % 8 == 0 && ldy % 8 == 0);
+  PGT_CHECK_ARG(C % 32 == 0 && C % 8 == 0 && C / 8 <= GN_APPLY_THREADS && ldx % 8 == 0 && ldy % 8 == 0);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfScope ps(PGT_PROF_NORM, 3.0 * F * (double)HW * C * 2, st);     // read, read, write (bf16)
   const int nchunks = gn_chunks(HW);
@@ -339,7 +340,7 @@ extern "C" int pgt_groupnorm_silu(const void* x, int ldx, int F, int HW, int C, 
   int ppb = (131072 / (C * 2));
   if (ppb < 16) ppb = 16;
   const int nblk = ceil_div(HW, ppb);
-  gn_apply_kernel<<<dim3(nblk, F), GN_THREADS, 0, st>>>(
+  gn_apply_kernel<<<dim3(nblk, F), GN_APPLY_THREADS, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C, ppb, ab, apply_silu,
       reinterpret_cast<__nv_bfloat16*>(y), ldy);
   PGT_LAUNCH_OK();

@@ -8,12 +8,11 @@ transformer (fp32, it decides the code indices).  Frames of a clip are contiguou
 frame-major token order of the global transformer (`archs/pgtformer_arch.py:614,640`) is the
 natural row order and no permute is ever materialised.
 
-Every op is a call into the C ABI; there is no PyTorch/CPU fallback — without the CUDA library
-construction fails.  The one exception, stated in DESIGN.md, is the BiSeNet parsing net (2.1 %
-of the FLOPs), which runs through cuDNN in round 1.
+Every op — including the BiSeNet parsing net, whose eval-mode BatchNorms are folded at load time — is a call
+into the C ABI; there is no PyTorch / cuDNN / CPU fallback: without the CUDA library construction fails.
 """
 import torch
-import torch.nn.functional as F
+import torch.nn.functional as F  # noqa: F401  (load-time weight padding only)
 
 from . import ops
 from .spec import Arch
@@ -109,9 +108,7 @@ class Engine:
             wi, bi = sd[p + '.in_proj_weight'].float(), sd[p + '.in_proj_bias'].float()
             w[p + '.qk.weight'], w[p + '.qk.bias'] = _pack_lin(wi[:2 * E]), bi[:2 * E].contiguous()
             w[p + '.v.weight'], w[p + '.v.bias'] = _pack_lin(wi[2 * E:]), bi[2 * E:].contiguous()
-        self.img_mean = torch.tensor([0.485, 0.456, 0.406], device=self.dev).view(1, 3, 1, 1)
-        self.img_std = torch.tensor([0.229, 0.224, 0.225], device=self.dev).view(1, 3, 1, 1)
-        self._cond = {k[len('conditionnet.'):]: v.float() for k, v in sd.items() if k.startswith('conditionnet.')}
+        self._repack_parsing()
 
     # ------------------------------------------------------------------ small helpers
     def _new(self, *shape, dtype=BF):
@@ -179,46 +176,115 @@ class Engine:
         sh = self._conv3(ef, p + '.shift.0', C, act=ops.ACT_LRELU02)
         return self._conv3(sh, p + '.shift.2', C, residual=dec, sft_scale=scale, sft_w=wgt)
 
-    # ------------------------------------------------------------------ parsing net (cuDNN, round 1)
-    def _bisenet(self, x):
-        sd = self._cond
-        conv = lambda p, t, s=1, pad=0: F.conv2d(t, sd[p + '.weight'], None, s, pad)
-        bn = lambda p, t: F.batch_norm(t, sd[p + '.running_mean'], sd[p + '.running_var'], sd[p + '.weight'], sd[p + '.bias'], False, 0.0, 1e-5)
-        cbr = lambda p, t, s=1, pad=1: F.relu(bn(p + '.bn', conv(p + '.conv', t, s, pad)))
+    # ------------------------------------------------------------------ parsing net (BiSeNet / ResNet18)
+    def _repack_parsing(self):
+        """Eval-mode BatchNorm folded into the preceding conv (w' = w*g/sqrt(v+eps), b' = beta - mean*g/sqrt(v+eps)),
+        then the usual kernel layouts (`archs/pgtformer_arch.py:40-397`)."""
+        sd, w = self._sd, self.w
+        P = 'conditionnet.'
 
-        def block(p, t, s):
-            r = F.relu(bn(p + '.bn1', conv(p + '.conv1', t, s, 1)))
-            r = bn(p + '.bn2', conv(p + '.conv2', r, 1, 1))
-            if (p + '.downsample.0.weight') in sd:
-                t = bn(p + '.downsample.1', conv(p + '.downsample.0', t, s))
-            return F.relu(t + r)
+        def fold(conv, bn):
+            wt = sd[P + conv + '.weight'].float()
+            if bn is None:
+                return wt, None
+            g, b = sd[P + bn + '.weight'].float(), sd[P + bn + '.bias'].float()
+            m, v = sd[P + bn + '.running_mean'].float(), sd[P + bn + '.running_var'].float()
+            s = g / torch.sqrt(v + 1e-5)
+            return wt * s.view(-1, 1, 1, 1), (b - m * s).contiguous()
 
-        def arm(p, t):
-            f = cbr(p + '.conv', t)
-            a = torch.sigmoid(bn(p + '.bn_atten', conv(p + '.conv_atten', f.mean((2, 3), keepdim=True))))
-            return f * a
+        def put(key, conv, bn, kind):
+            wt, bias = fold(conv, bn)
+            w['bn.' + key + '.weight'] = {'c3': _pack_conv, 'up': _pack_up2x, 'lin': _pack_lin,
+                                          'raw': lambda t: t.contiguous()}[kind](wt)
+            if bias is not None:
+                w['bn.' + key + '.bias'] = bias
 
-        H, W = x.shape[2:]
-        t = F.max_pool2d(F.relu(bn('cp.resnet.bn1', conv('cp.resnet.conv1', x, 2, 3))), 3, 2, 1)
+        put('stem', 'cp.resnet.conv1', 'cp.resnet.bn1', 'raw')
+        for li in (1, 2, 3, 4):
+            for bi in (0, 1):
+                p = 'cp.resnet.layer%d.%d' % (li, bi)
+                put(p + '.c1', p + '.conv1', p + '.bn1', 'c3')
+                put(p + '.c2', p + '.conv2', p + '.bn2', 'c3')
+                if (P + p + '.downsample.0.weight') in sd:
+                    put(p + '.ds', p + '.downsample.0', p + '.downsample.1', 'lin')
+        for a in ('arm16', 'arm32'):
+            put(a + '.conv', 'cp.%s.conv.conv' % a, 'cp.%s.conv.bn' % a, 'c3')
+            put(a + '.att', 'cp.%s.conv_atten' % a, 'cp.%s.bn_atten' % a, 'lin')
+        put('head32', 'cp.conv_head32.conv', 'cp.conv_head32.bn', 'up')
+        put('head16', 'cp.conv_head16.conv', 'cp.conv_head16.bn', 'up')
+        put('avg', 'cp.conv_avg.conv', 'cp.conv_avg.bn', 'lin')
+        put('ffm.blk', 'ffm.convblk.conv', 'ffm.convblk.bn', 'lin')
+        put('ffm.c1', 'ffm.conv1', None, 'lin')
+        put('ffm.c2', 'ffm.conv2', None, 'lin')
+        for o in ('conv_out', 'conv_out16', 'conv_out32'):
+            put(o + '.conv', o + '.conv.conv', o + '.conv.bn', 'c3')
+            put(o + '.out', o + '.conv_out', None, 'lin')
+
+    def _pconv(self, x, key, cout, stride=1, **kw):
+        Fr, H, W, _ = x.shape
+        out = self._new(Fr, H // stride, W // stride, cout)
+        return ops.conv(x, self.w['bn.' + key + '.weight'], cout, out, stride=stride, pad_lo=1,
+                        bias=self.w.get('bn.' + key + '.bias'), **kw)
+
+    def _plin(self, x, key, n, act=ops.ACT_NONE, out=None):
+        if out is None:
+            out = self._new(*x.shape[:-1], n)
+        return ops.linear(x, self.w['bn.' + key + '.weight'], out, bias=self.w.get('bn.' + key + '.bias'), N=n, act=act)
+
+    def _basic_block(self, x, p, cout, stride):
+        """BasicBlock (`archs/pgtformer_arch.py:41-68`): relu(bn1(conv1)) -> bn2(conv2) ; relu(shortcut + residual)."""
+        r = self._pconv(x, p + '.c1', cout, stride, act=ops.ACT_RELU)
+        if ('bn.' + p + '.ds.weight') in self.w:
+            Fr, H, W, cin = x.shape
+            sc = self._new(Fr, H // stride, W // stride, cout)
+            ops.conv(x, self.w['bn.' + p + '.ds.weight'], cout, sc, ksize=1, stride=stride, pad_lo=0,
+                     bias=self.w['bn.' + p + '.ds.bias'])
+        else:
+            sc = x
+        return self._pconv(r, p + '.c2', cout, 1, act=ops.ACT_RELU, residual=sc, relu_after_res=True)
+
+    def parsing_net(self, x):
+        """BiSeNet.forward (`archs/pgtformer_arch.py:365-379`) on the raw [F,3,H,W] image (ImageNet normalisation fused
+        into the stem) -> conditioning map [F, H/16, W/16, 64] bf16 (57 channels used, zero padded)."""
+        Fr, _, H, W = x.shape
+        w = self.w
+        t = ops.stem7x7(x, (0.485, 0.456, 0.406), (0.229, 0.224, 0.225), w['bn.stem.weight'], w['bn.stem.bias'],
+                        self._new(Fr, H // 2, W // 2, 64))
+        t = ops.maxpool3x3s2(t, self._new(Fr, H // 4, W // 4, 64))
         feats = []
-        for li, s in ((1, 1), (2, 2), (3, 2), (4, 2)):
-            t = block('cp.resnet.layer%d.0' % li, t, s)
-            t = block('cp.resnet.layer%d.1' % li, t, 1)
+        for li, cout, stride in ((1, 64, 1), (2, 128, 2), (3, 256, 2), (4, 512, 2)):
+            t = self._basic_block(t, 'cp.resnet.layer%d.0' % li, cout, stride)
+            t = self._basic_block(t, 'cp.resnet.layer%d.1' % li, cout, 1)
             feats.append(t)
         f8, f16, f32 = feats[1], feats[2], feats[3]
-        avg = cbr('cp.conv_avg', f32.mean((2, 3), keepdim=True), 1, 0)
-        u32 = cbr('cp.conv_head32', F.interpolate(arm('cp.arm32', f32) + avg, f16.shape[2:], mode='nearest'))
-        u16 = cbr('cp.conv_head16', F.interpolate(arm('cp.arm16', f16) + u32, f8.shape[2:], mode='nearest'))
-        fc = cbr('ffm.convblk', torch.cat([f8, u16], 1), 1, 0)
-        at = torch.sigmoid(conv('ffm.conv2', F.relu(conv('ffm.conv1', fc.mean((2, 3), keepdim=True)))))
-        fuse = fc * at + fc
-        o0 = conv('conv_out.conv_out', cbr('conv_out.conv', fuse))
-        o1 = conv('conv_out16.conv_out', cbr('conv_out16.conv', u16))
-        o2 = conv('conv_out32.conv_out', cbr('conv_out32.conv', u32))
-        size = (H // 16, W // 16)
-        o0 = F.interpolate(o0, size, mode='bilinear', align_corners=True)
-        o1 = F.interpolate(o1, size, mode='bilinear', align_corners=True)
-        return torch.cat([o0, o1, o2], 1)
+        # context path (:228-249)
+        avg = self._plin(ops.global_avgpool(f32, self._new(Fr, 512)), 'avg', 128, act=ops.ACT_RELU)
+        a32 = self._pconv(f32, 'arm32.conv', 128, act=ops.ACT_RELU)
+        att = self._plin(ops.global_avgpool(a32, self._new(Fr, 128)), 'arm32.att', 128, act=ops.ACT_SIGMOID)
+        s32 = ops.channel_affine(a32, att, self._new(*a32.shape), addv=avg)
+        u32 = ops.conv_up2x(s32, w['bn.head32.weight'], 128, self._new(Fr, H // 16, W // 16, 128), bias=w['bn.head32.bias'],
+                            act=ops.ACT_RELU)
+        a16 = self._pconv(f16, 'arm16.conv', 128, act=ops.ACT_RELU)
+        att = self._plin(ops.global_avgpool(a16, self._new(Fr, 128)), 'arm16.att', 128, act=ops.ACT_SIGMOID)
+        s16 = ops.channel_affine(a16, att, self._new(*a16.shape), addm=u32)
+        u16 = ops.conv_up2x(s16, w['bn.head16.weight'], 128, self._new(Fr, H // 8, W // 8, 128), bias=w['bn.head16.bias'],
+                            act=ops.ACT_RELU)
+        # feature fusion (:324-334)
+        cat = self._new(Fr, H // 8, W // 8, 256)
+        ops.copy2d(f8, cat[..., :128])
+        ops.copy2d(u16, cat[..., 128:])
+        fc = self._plin(cat, 'ffm.blk', 256, act=ops.ACT_RELU)
+        at = self._plin(self._plin(ops.global_avgpool(fc, self._new(Fr, 256)), 'ffm.c1', 64, act=ops.ACT_RELU),
+                        'ffm.c2', 256, act=ops.ACT_SIGMOID)
+        fuse = ops.channel_affine(fc, at, self._new(*fc.shape), plus_one=True)
+        # three 19-class heads (:147-150) -> bilinear(align_corners) to H/16 and concatenate
+        o0 = self._plin(self._pconv(fuse, 'conv_out.conv', 256, act=ops.ACT_RELU), 'conv_out.out', 19,
+                        out=self._new(Fr, H // 8, W // 8, 32))
+        o1 = self._plin(self._pconv(u16, 'conv_out16.conv', 64, act=ops.ACT_RELU), 'conv_out16.out', 19,
+                        out=self._new(Fr, H // 8, W // 8, 32))
+        o2 = self._plin(self._pconv(u32, 'conv_out32.conv', 64, act=ops.ACT_RELU), 'conv_out32.out', 19,
+                        out=self._new(Fr, H // 16, W // 16, 32))
+        return ops.assemble_cond(o0, o1, o2, self._new(Fr, H // 16, W // 16, 64))
 
     # ------------------------------------------------------------------ encoder / decoder
     def encoder(self, x):
@@ -269,13 +335,8 @@ class Engine:
         """BiSeNet parsing features -> convpos 1x1 -> positional term [T, 512] bf16
         (`archs/pgtformer_arch.py:606-614`)."""
         Fr, _, H, W = x.shape
-        hh, ww = H // 16, W // 16
-        with torch.autocast('cuda', dtype=BF):           # cuDNN bf16 tensor-core path for the parsing net (round 1)
-            cond = self._bisenet(((x - self.img_mean) / self.img_std).contiguous(memory_format=torch.channels_last))
-        cond = cond.float()
-        cond_nhwc = torch.zeros(Fr, hh, ww, 64, dtype=BF, device=self.dev)
-        ops.nchw_to_nhwc(cond.contiguous(), cond_nhwc)
-        return self._lin(cond_nhwc.view(Fr * hh * ww, 64), 'convpos', 512, K=57)
+        cond = self.parsing_net(x)
+        return self._lin(cond.view(Fr * (H // 16) * (W // 16), 64), 'convpos', 512, K=57)
 
     def global_transformer(self, lq, pos, clips):
         """feat_emb + 9 x TransformerSALayer + idx_pred_layer (`archs/pgtformer_arch.py:638-649`,

@@ -43,8 +43,10 @@ def _rows(t):
     return rows, C, ld
 
 
-def make_epilogue(out, bias=None, act=ACT_NONE, residual=None, sft_scale=None, sft_w=0.0, nchw=False):
+def make_epilogue(out, bias=None, act=ACT_NONE, residual=None, sft_scale=None, sft_w=0.0, nchw=False,
+                  relu_after_res=False):
     ep = Epilogue()
+    ep.flags = 1 if relu_after_res else 0
     ep.bias = bias.data_ptr() if bias is not None else None
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous()
@@ -67,7 +69,7 @@ def make_epilogue(out, bias=None, act=ACT_NONE, residual=None, sft_scale=None, s
     return ep
 
 
-def linear(a, w, out, bias=None, act=ACT_NONE, residual=None, K=None, N=None):
+def linear(a, w, out, bias=None, act=ACT_NONE, residual=None, K=None, N=None, relu_after_res=False):
     """out[T,N] = act(a[T,K] @ w[N,K]^T + bias) (+ residual).  a, w bf16; out bf16 / fp32."""
     lib = L.load()
     M, Ka, lda = _rows(a)
@@ -76,19 +78,19 @@ def linear(a, w, out, bias=None, act=ACT_NONE, residual=None, K=None, N=None):
     N = N if N is not None else Nw
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.stride(1) == 1
     assert _rows(out)[0] == M and out.shape[-1] >= N
-    ep = make_epilogue(out, bias, act, residual)
+    ep = make_epilogue(out, bias, act, residual, relu_after_res=relu_after_res)
     L.check(lib.pgt_linear_bf16(_p(a), lda, _p(w), w.stride(0), M, N, K, ctypes.byref(ep), _stream()))
     return out
 
 
 def conv(x, wp, cout, out, ksize=3, stride=1, pad_lo=1, bias=None, act=ACT_NONE, residual=None, sft_scale=None,
-         sft_w=0.0, nchw=False):
+         sft_w=0.0, nchw=False, relu_after_res=False):
     """Implicit-GEMM conv on [F,H,W,Cin] bf16 with packed weights wp [>=cout, k*k*CinPad]."""
     lib = L.load()
     F, H, W, Cin = x.shape
     assert x.dtype == torch.bfloat16 and x.stride(3) == 1 and x.stride(1) == W * x.stride(2) and \
         (F == 1 or x.stride(0) == H * x.stride(1))
-    ep = make_epilogue(out, bias, act, residual, sft_scale, sft_w, nchw)
+    ep = make_epilogue(out, bias, act, residual, sft_scale, sft_w, nchw, relu_after_res)
     L.check(lib.pgt_conv_bf16(_p(x), F, H, W, Cin, x.stride(2), _p(wp), wp.stride(0), cout, ksize, stride, pad_lo,
                               ctypes.byref(ep), _stream()))
     return out
@@ -187,6 +189,49 @@ def adain(q, style, out, eps=1e-5):
     L.check(lib.pgt_adain(_p(q), _rows(q)[2], _dt(q), _p(style), _rows(style)[2], F, HW, C, eps, _p(out),
                           _rows(out)[2], _stream()))
     return out
+
+
+def stem7x7(x_nchw, mean3, std3, w, bias, out):
+    """mean3 / std3: python sequences of 3 floats (host)."""
+    lib = L.load()
+    F, C, H, W = x_nchw.shape
+    assert C == 3 and x_nchw.dtype == torch.float32 and x_nchw.is_contiguous() and w.is_contiguous()
+    m = (ctypes.c_float * 3)(*[float(v) for v in mean3])
+    s = (ctypes.c_float * 3)(*[float(v) for v in std3])
+    L.check(lib.pgt_stem7x7_rgb(_p(x_nchw), F, H, W, m, s, _p(w), _p(bias), _p(out), _rows(out)[2], _stream()))
+    return out
+
+
+def maxpool3x3s2(x, out):
+    lib = L.load()
+    F, H, W, C = x.shape
+    L.check(lib.pgt_maxpool3x3s2(_p(x), _rows(x)[2], F, H, W, C, _p(out), _rows(out)[2], _stream()))
+    return out
+
+
+def global_avgpool(x, out):
+    lib = L.load()
+    F, H, W, C = x.shape
+    L.check(lib.pgt_global_avgpool(_p(x), _rows(x)[2], F, H * W, C, _p(out), out.stride(0), _stream()))
+    return out
+
+
+def channel_affine(x, scale, out, plus_one=False, addv=None, addm=None):
+    lib = L.load()
+    F, H, W, C = x.shape
+    L.check(lib.pgt_channel_affine(_p(x), _rows(x)[2], F, H * W, C, _p(scale), scale.stride(0), int(plus_one),
+                                   _p(addv), addv.stride(0) if addv is not None else 0,
+                                   _p(addm), _rows(addm)[2] if addm is not None else 0, _p(out), _rows(out)[2], _stream()))
+    return out
+
+
+def assemble_cond(o0, o1, o2, cond, ncls=19):
+    lib = L.load()
+    F, h8, w8, _ = o0.shape
+    _, h16, w16, _ = o2.shape
+    L.check(lib.pgt_assemble_cond(_p(o0), _rows(o0)[2], _p(o1), _rows(o1)[2], _p(o2), _rows(o2)[2], F, h8, w8, h16, w16,
+                                  ncls, _p(cond), _rows(cond)[2], _stream()))
+    return cond
 
 
 def upsample2x(x, out):

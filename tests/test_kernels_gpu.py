@@ -381,3 +381,50 @@ def test_layout_kernels():
     f32b = torch.empty(2, 8, 8, 64, dtype=torch.float32, device=DEV)
     o.nhwc_to_f32(a.to(DEV), f32b, False)
     assert torch.equal(f32b.cpu(), a.float())
+
+
+# ------------------------------------------------------------------------------------ parsing-branch kernels
+def test_stem7x7_maxpool_avgpool_affine_assemble():
+    o = ops()
+    Fr, H, W = 3, 64, 64
+    x = torch.rand(Fr, 3, H, W, generator=torch.Generator().manual_seed(130))
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    w, b = rnd((64, 3, 7, 7), 131, 147 ** -0.5), rnd((64,), 132, 0.1)
+    y = torch.empty(Fr, H // 2, W // 2, 64, dtype=torch.bfloat16, device=DEV)
+    o.stem7x7(x.to(DEV), mean, std, w.to(DEV), b.to(DEV), y)
+    nx = (x - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+    ref = F.relu(F.conv2d(nx, w, b, stride=2, padding=3)).permute(0, 2, 3, 1)
+    check_close(y, ref, 'stem7x7', bf16_out=True)
+    mp = torch.empty(Fr, H // 4, W // 4, 64, dtype=torch.bfloat16, device=DEV)
+    o.maxpool3x3s2(y, mp)
+    refmp = F.max_pool2d(y.float().cpu().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(mp.float().cpu(), refmp)
+    ap = torch.empty(Fr, 64, dtype=torch.bfloat16, device=DEV)
+    o.global_avgpool(mp, ap)
+    check_close(ap, refmp.mean((1, 2)), 'avgpool', bf16_out=True)
+    sc, av = bf(rnd((Fr, 64), 133)), bf(rnd((Fr, 64), 134))
+    am = bf(rnd((Fr, H // 4, W // 4, 64), 135))
+    out = torch.empty_like(mp)
+    o.channel_affine(mp, sc.to(DEV), out, plus_one=True, addv=av.to(DEV), addm=am.to(DEV))
+    refa = refmp * (sc.float()[:, None, None, :] + 1) + av.float()[:, None, None, :] + am.float()
+    check_close(out, refa, 'channel_affine', bf16_out=True)
+    o0, o1 = bf(rnd((Fr, 16, 16, 32), 136)), bf(rnd((Fr, 16, 16, 32), 137))
+    o2 = bf(rnd((Fr, 8, 8, 32), 138))
+    cond = torch.empty(Fr, 8, 8, 64, dtype=torch.bfloat16, device=DEV)
+    o.assemble_cond(o0.to(DEV), o1.to(DEV), o2.to(DEV), cond)
+    up = lambda t: F.interpolate(t.float()[..., :19].permute(0, 3, 1, 2), (8, 8), mode='bilinear', align_corners=True).permute(0, 2, 3, 1)
+    refc = torch.cat([up(o0), up(o1), o2.float()[..., :19], torch.zeros(Fr, 8, 8, 7)], -1)
+    check_close(cond, refc, 'assemble_cond', bf16_out=True)
+
+
+def test_conv_relu_after_residual():
+    o = ops()
+    Fr, H, W, C = 3, 16, 16, 256
+    x = bf(rnd((Fr, H, W, C), 140))
+    w = bf(rnd((C, C, 3, 3), 141, (9 * C) ** -0.5)).float()
+    b = rnd((C,), 142, 0.1)
+    res = bf(rnd((Fr, H, W, C), 143))
+    out = torch.empty(Fr, H, W, C, dtype=torch.bfloat16, device=DEV)
+    o.conv(x.to(DEV), pack_conv_weight(w).to(DEV), C, out, bias=b.to(DEV), act=o.ACT_RELU, residual=res.to(DEV),
+           relu_after_res=True)
+    check_close(out, F.relu(conv_ref(x, w, b) + res.float()), 'conv relu-after-residual', bf16_out=True)
