@@ -101,7 +101,9 @@ def cpu_oracle_clips_per_s(H, warmup, steps):
     from oracle import pgt_oracle as O
     from pgtformer_b200.spec import build_spec
     from pgtformer_b200.weights import synth_state_dict
-    torch.set_num_threads(os.cpu_count())
+    # all the host threads that help: on the 2x32-core GPU boxes oneDNN/OpenMP is fastest at 16-32 threads and
+    # collapses (100x slower) at 128 — measured with tools/cpu_threads.py (256^2 clip: 1.5 s @16-32, 2.5 s @64, 118 s @128)
+    torch.set_num_threads(min(os.cpu_count() or 1, 32))
     arch, spec = build_spec(load_network_g())
     sd = synth_state_dict(spec, 0)
     x = torch.rand(3, 3, H, H, generator=torch.Generator().manual_seed(1))
