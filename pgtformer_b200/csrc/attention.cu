@@ -3,6 +3,8 @@
 //   * shifted-window spatio-temporal attention, 3x4x4 windows (N = 48), roll / partition / reverse and the
 //     {0,-100} shift mask done as index math, relative-position bias from a [heads,48,48] table;
 //   * global multi-head flash attention (online softmax, K/V tiles double-buffered with cp.async).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pgt {
@@ -281,6 +283,9 @@ mha_fwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16
   }
 }
 
+int mha_tc_launch(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int clips, int L, int heads,
+                  int d, void* out, int ldo, cudaStream_t stream);      // mha_tc.cu (tcgen05 path)
+
 }  // namespace pgt
 
 using namespace pgt;
@@ -324,6 +329,12 @@ extern "C" int pgt_mha_fwd(const void* q, int ldq, const void* k, int ldk, const
   PGT_CHECK_ARG(q && k && v && out && clips > 0 && L > 0 && heads > 0);
   PGT_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0);
   if (d != 64) return PGT_ERR_UNSUPPORTED;
+  static const bool no_tc = getenv("PGT_MHA_NO_TC") != nullptr;
+  if (!no_tc) {
+    ProfScope pst(PGT_PROF_MHA, 4.0 * (double)L * L * d * heads * clips, static_cast<cudaStream_t>(stream), "mha_tc");
+    const int rc = mha_tc_launch(q, ldq, k, ldk, v, ldv, clips, L, heads, d, out, ldo, static_cast<cudaStream_t>(stream));
+    if (rc != PGT_ERR_UNSUPPORTED) return rc;        // shapes the tcgen05 kernel does not cover use the mma.sync kernel
+  }
   dim3 grid(ceil_div(L, FA_BM), heads, clips);
   const size_t smem = (size_t)4 * FA_BN * (64 + 8) * 2;
   ProfScope ps(PGT_PROF_MHA, 4.0 * (double)L * L * d * heads * clips, static_cast<cudaStream_t>(stream));

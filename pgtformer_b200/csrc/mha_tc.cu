@@ -1,0 +1,297 @@
+// Global multi-head attention forward on tcgen05 (flash-attention, d = 64, no mask), sm_100a.
+//
+// One CTA = one (clip, head) and TWO 128-query tiles (ping-pong groups G0/G1) that share the K/V stream:
+//   warp 0      TMA producer: Q tiles once, then K_j / V_j tiles (128 keys x 64, 128B swizzle) through a 3-deep ring
+//   warp 1      single-thread tcgen05.mma issuer:  S_g = Q_g K_j^T (128x128x64, fp32 in TMEM)  and
+//               O_g = P_g V_j (128x64x128; P_g bf16 in swizzled smem, V_j consumed MN-major straight from its TMA tile)
+//   warps 2..5  softmax group 0, warps 6..9 softmax group 1 (thread = query row): tcgen05.ld S, online softmax in
+//               fp32 (exp2 on MUFU), P -> smem, then O_reg = alpha * O_reg + (P V) read back from TMEM.
+// While group g runs its softmax the tensor pipe works for the other group (S/PV of G1 overlap softmax of G0).
+// TMEM: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384).
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace pgt {
+
+constexpr int FT_D = 64;
+constexpr int FT_BM = 128;                 // queries per group
+constexpr int FT_BN = 128;                 // keys per tile
+constexpr int FT_NST = 3;                  // K/V ring depth
+constexpr int FT_TILE = FT_BN * FT_D * 2;  // 16 KB: one 128 x 64 bf16 tile
+constexpr int FT_THREADS = 64 + 256;
+constexpr int FT_SMEM = 2 * FT_TILE /*Q*/ + FT_NST * 2 * FT_TILE /*K,V*/ + 2 * 2 * FT_TILE /*P*/ + 256 + 1024;
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// MN-major (the N x K operand is stored K-rows x N-contiguous), 128B swizzle: 8 K-rows per 1024 B atom.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((16384 >> 4) & 0x3FFF) << 16;    // LBO: stride between 64-element MN atoms (single atom here)
+  d |= static_cast<uint64_t>((1024 >> 4) & 0x3FFF) << 32;     // SBO: stride between 8-row K groups
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(FT_THREADS, 1)
+mha_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+              const __grid_constant__ CUtensorMap tmV, int L, __nv_bfloat16* __restrict__ out, int ldo) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // [2][16 KB]
+  uint8_t* sK = sQ + 2 * FT_TILE;                       // [NST][16 KB]
+  uint8_t* sV = sK + FT_NST * FT_TILE;                  // [NST][16 KB]
+  uint8_t* sP = sV + FT_NST * FT_TILE;                  // [2 groups][2 key halves][16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * FT_TILE);
+  uint64_t* q_full = bars;                              // [1]
+  uint64_t* kv_full = bars + 1;                         // [NST]
+  uint64_t* kv_empty = kv_full + FT_NST;                // [NST]
+  uint64_t* s_full = kv_empty + FT_NST;                 // [2]
+  uint64_t* p_full = s_full + 2;                        // [2]
+  uint64_t* o_full = p_full + 2;                        // [2]
+  uint64_t* o_empty = o_full + 2;                       // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, clip = blockIdx.z;
+  const int q0 = clip * L + blockIdx.x * 2 * FT_BM;     // first query row (global token index) of this CTA
+  const int kv0 = clip * L;
+  const int NT = L / FT_BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < FT_NST; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&p_full[g], 128);
+      mbar_init(&o_full[g], 1);
+      mbar_init(&o_empty[g], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<512>(tmem_ptr);
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, 2 * FT_TILE);
+      tma_load_2d(sQ, &tmQ, q_full, h * FT_D, q0);
+      tma_load_2d(sQ + FT_TILE, &tmQ, q_full, h * FT_D, q0 + FT_BM);
+    }
+    __syncwarp();
+    int st = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < NT; ++j) {
+      mbar_wait(&kv_empty[st], ph ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&kv_full[st], 2 * FT_TILE);
+        tma_load_2d(sK + st * FT_TILE, &tmK, &kv_full[st], h * FT_D, kv0 + j * FT_BN);
+        tma_load_2d(sV + st * FT_TILE, &tmV, &kv_full[st], h * FT_D, kv0 + j * FT_BN);
+      }
+      __syncwarp();
+      if (++st == FT_NST) { st = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_s = umma_idesc_bf16(FT_BM, FT_BN);                   // S: A,B K-major
+    constexpr uint32_t idesc_o = umma_idesc_bf16(FT_BM, FT_D) | (1u << 16);       // O: B (= V) MN-major
+    auto issue_s = [&](int g, int st) {
+      const uint64_t da = umma_desc_k_sw128(smem_u32(sQ + g * FT_TILE));
+      const uint64_t db = umma_desc_k_sw128(smem_u32(sK + st * FT_TILE));
+#pragma unroll
+      for (int k = 0; k < FT_D / 16; ++k) umma_bf16_ss(tmem_base + g * FT_BN, da + 2 * k, db + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+      umma_commit(&s_full[g]);
+    };
+    auto issue_o = [&](int g, int st) {
+#pragma unroll
+      for (int kt = 0; kt < 2; ++kt) {
+        const uint64_t da = umma_desc_k_sw128(smem_u32(sP + (g * 2 + kt) * FT_TILE));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // 16 keys per step: +32 B inside P's swizzled row (K-major), +16 key rows = 2048 B in the V tile (MN-major)
+          const uint64_t db = umma_desc_mn_sw128(smem_u32(sV + st * FT_TILE + (kt * 64 + k * 16) * 128));
+          umma_bf16_ss(tmem_base + 256 + g * FT_D, da + 2 * k, db, idesc_o, (kt | k) != 0 ? 1u : 0u);
+        }
+      }
+      umma_commit(&o_full[g]);
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    if (elect_one()) { issue_s(0, 0); issue_s(1, 0); }
+    __syncwarp();
+    int st = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < NT; ++j) {
+      const uint32_t par = j & 1;
+      int nst = st + 1;
+      uint32_t nph = ph;
+      if (nst == FT_NST) { nst = 0; nph ^= 1; }
+      for (int g = 0; g < 2; ++g) {
+        mbar_wait(&p_full[g], par);                    // P_g(j) is in smem and S_g has been read out
+        mbar_wait(&o_empty[g], par ^ 1);               // O_g scratch accumulator has been drained
+        if (g == 0 && j + 1 < NT) mbar_wait(&kv_full[nst], nph);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_o(g, st);
+          if (g == 1) umma_commit(&kv_empty[st]);      // every MMA reading K_j / V_j has been issued
+          if (j + 1 < NT) issue_s(g, nst);
+        }
+        __syncwarp();
+      }
+      st = nst; ph = nph;
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax / accumulate groups
+    const int g = (warp - 2) >> 2;
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;                      // query row inside the group's tile
+    const uint32_t lane_base = uint32_t(quad * 32) << 16;
+    const uint32_t tS = tmem_base + lane_base + g * FT_BN;
+    const uint32_t tO = tmem_base + lane_base + 256 + g * FT_D;
+    uint8_t* prow = sP + g * 2 * FT_TILE + r * 128;
+    const float sl2 = 0.125f * 1.4426950408889634f;     // d^-1/2 * log2(e)
+    float m = -1e30f, l = 0.f;
+    float o[FT_D];
+#pragma unroll
+    for (int i = 0; i < FT_D; ++i) o[i] = 0.f;
+    for (int j = 0; j < NT; ++j) {
+      const uint32_t par = j & 1;
+      mbar_wait(&s_full[g], par);
+      tc_fence_after();
+      // pass 1: row maximum
+      float mx = -1e30f;
+#pragma unroll 1
+      for (int c = 0; c < FT_BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = fast_exp2((m - m_new) * sl2);
+      const float mb = m_new * sl2;
+      m = m_new;
+      // pass 2: p = 2^(s*sl2 - mb), row sum, bf16 P into the swizzled A-operand tile
+      float rs = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < FT_BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + c, v);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          pv[i] = fast_exp2(fmaf(__uint_as_float(v[i]), sl2, -mb));
+          rs += pv[i];
+        }
+        uint8_t* dst = prow + (c >> 6) * FT_TILE;        // key half (64 keys = one 128 B row of the sub-tile)
+        const int ch0 = (c & 63) >> 3;                   // first 16-byte chunk of this 32-key run
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = pack_bf16x2(pv[8 * q + 0], pv[8 * q + 1]);
+          u.y = pack_bf16x2(pv[8 * q + 2], pv[8 * q + 3]);
+          u.z = pack_bf16x2(pv[8 * q + 4], pv[8 * q + 5]);
+          u.w = pack_bf16x2(pv[8 * q + 6], pv[8 * q + 7]);
+          *reinterpret_cast<uint4*>(dst + (((ch0 + q) ^ (r & 7)) << 4)) = u;
+        }
+      }
+      l = l * alpha + rs;
+      tc_fence_before();
+      fence_proxy_async();                               // P (generic writes) -> visible to the tensor core's smem reads
+      mbar_arrive(&p_full[g]);
+      // O_reg = alpha * O_reg + P V
+      mbar_wait(&o_full[g], par);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < FT_D; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tO + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], alpha, __uint_as_float(v[i]));
+      }
+      tc_fence_before();
+      mbar_arrive(&o_empty[g]);
+    }
+    const float inv = 1.f / l;
+    __nv_bfloat16* orow = out + (size_t)(q0 + g * FT_BM + r) * ldo + h * FT_D;
+#pragma unroll
+    for (int q = 0; q < FT_D / 8; ++q) {
+      uint4 u;
+      u.x = pack_bf16x2(o[8 * q + 0] * inv, o[8 * q + 1] * inv);
+      u.y = pack_bf16x2(o[8 * q + 2] * inv, o[8 * q + 3] * inv);
+      u.z = pack_bf16x2(o[8 * q + 4] * inv, o[8 * q + 5] * inv);
+      u.w = pack_bf16x2(o[8 * q + 6] * inv, o[8 * q + 7] * inv);
+      reinterpret_cast<uint4*>(orow)[q] = u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+static int encode_rows_map(CUtensorMap* map, const void* base, int ld, long long rows, int cols) {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return PGT_ERR_DRIVER;
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {FT_D, FT_BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PGT_OK : PGT_ERR_DRIVER;
+}
+
+// Returns PGT_ERR_UNSUPPORTED when the shape is not covered (caller falls back to the mma.sync kernel).
+int mha_tc_launch(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int clips, int L, int heads,
+                  int d, void* out, int ldo, cudaStream_t stream) {
+  if (d != FT_D || L % (2 * FT_BM) != 0) return PGT_ERR_UNSUPPORTED;
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al(q) || !al(k) || !al(v) || !al(out) || ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8) return PGT_ERR_UNSUPPORTED;
+  CUtensorMap tq, tk, tv;
+  const long long rows = (long long)clips * L;
+  int rc = encode_rows_map(&tq, q, ldq, rows, heads * d);
+  if (rc == PGT_OK) rc = encode_rows_map(&tk, k, ldk, rows, heads * d);
+  if (rc == PGT_OK) rc = encode_rows_map(&tv, v, ldv, rows, heads * d);
+  if (rc != PGT_OK) return rc;
+  static bool attr = false;
+  if (!attr) {
+    PGT_CUDA_OK(cudaFuncSetAttribute(mha_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+    attr = true;
+  }
+  dim3 grid(L / (2 * FT_BM), heads, clips);
+  mha_tc_kernel<<<grid, FT_THREADS, FT_SMEM, stream>>>(tq, tk, tv, L, reinterpret_cast<__nv_bfloat16*>(out), ldo);
+  PGT_LAUNCH_OK();
+  return PGT_OK;
+}
+
+}  // namespace pgt

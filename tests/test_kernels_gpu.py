@@ -345,7 +345,7 @@ def test_window_attention_core(C, H, W, clips, shifted):
     check_close(out, ref.reshape(T, C), 'window attention', bf16_out=True, rel=4e-3)
 
 
-@pytest.mark.parametrize('L,clips', [(192, 2), (3072, 1), (48, 1), (200, 1)])
+@pytest.mark.parametrize('L,clips', [(192, 2), (3072, 1), (48, 1), (200, 1), (768, 2), (256, 3)])
 def test_mha_fwd(L, clips):
     o = ops()
     heads, d, E = 8, 64, 512
