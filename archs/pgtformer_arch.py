@@ -15,6 +15,8 @@ pgtformer_b200.engine.Engine; kernel-layout weight copies are derived caches reb
 load_state_dict() / .to().  Inference only (the reference's training loop is not in its repo,
 SURVEY F12); there is no CPU path.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -143,6 +145,8 @@ class PGTFormer(TDCRQVAE3):
         self._setup(g)
         self.codebook_size = self.arch.n_embed
         self.quantizer_depth = self.arch.code_shape[-1]
+        # replay the forward from a CUDA graph (static output tensors!) — opt-in: attribute or PGT_CUDA_GRAPH=1
+        self.cuda_graph = os.environ.get('PGT_CUDA_GRAPH', '0') == '1'
 
     def forward(self, x, w=None, detach_16=True, code_only=None, adain=None, force_codes=None):
         """`archs/pgtformer_arch.py:598-714`: returns (out, logits, lq_feat_nhwc), or
@@ -153,6 +157,8 @@ class PGTFormer(TDCRQVAE3):
             w = self.w
         if adain is None:
             adain = self.adain
+        if self.cuda_graph and not code_only and force_codes is None:
+            return self.engine().forward_graphed(x, w=w, adain=bool(adain))
         return self.engine().forward(x, w=w, adain=bool(adain), code_only=bool(code_only), force_codes=force_codes)
 
     def forward_vq(self, input, code_only=False):

@@ -145,6 +145,7 @@ def main():
     ap.add_argument('--clips', type=int, default=16, help='clips per GPU per step')
     ap.add_argument('--size', type=int, default=512)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--graph', action='store_true', help='replay the forward from a CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -168,6 +169,7 @@ def main():
     kw.pop('type')
     model = PGTFormer(**kw).to(dev)
     model.eval()
+    model.cuda_graph = bool(args.graph)
     b, H = args.clips, args.size
     g = torch.Generator().manual_seed(1 + rank)
     x_host = torch.rand(b * 3, 3, H, H, generator=g).pin_memory()
@@ -223,6 +225,7 @@ def main():
 
     # roofline of the dominant kernel: separate profiled pass (events around every launch of the class)
     torch.cuda.synchronize()
+    model.cuda_graph = False                                   # the profiler brackets individual launches
     ops.profile_begin()
     for _ in range(args.steps):
         model(x_dev, w=1, adain=True)
@@ -244,7 +247,7 @@ def main():
                                    'random-init pgtformer-base' % (b, H, H, '2' if world == 1 else '3'),
                        'clips_per_gpu': b, 'size': H, 'global_clips': world * b, 'parallelism': 'dp%d' % world,
                        'l2_policy': 'inputs and activations (GBs per step) exceed the 126 MB L2; no flush needed',
-                       'flops_per_clip': flops_per_clip(H)},
+                       'flops_per_clip': flops_per_clip(H), 'cuda_graph': bool(args.graph)},
             'e2e': {'value': e2e_val, 'unit': 'clips/s', 'ms_per_step': ms_e2e / args.steps,
                     'h2d_bytes_per_step': x_host.numel() * 4, 'd2h_bytes_per_step': out_host.numel() * 4},
             'gpu_launches': launches,

@@ -201,3 +201,21 @@ def test_batch_equals_per_clip(model):
     out0 = model(x[:3], w=1, adain=True, force_codes=codes[:3])[0]
     out1 = model(x[3:], w=1, adain=True, force_codes=codes[3:])[0]
     assert torch.equal(out, torch.cat([out0, out1], 0))
+
+
+def test_cuda_graph_replay_matches_eager(model):
+    x = torch.rand(3, 3, 128, 128, generator=torch.Generator().manual_seed(12)).to(DEV)
+    ref = [t.clone() for t in model(x, w=1, adain=True)]
+    model.cuda_graph = True
+    try:
+        for _ in range(2):
+            got = model(x, w=1, adain=True)
+            for a, b in zip(got, ref):
+                assert torch.equal(a, b)
+        x2 = torch.rand(3, 3, 128, 128, generator=torch.Generator().manual_seed(13)).to(DEV)
+        got2 = [t.clone() for t in model(x2, w=1, adain=True)]
+    finally:
+        model.cuda_graph = False
+    ref2 = model(x2, w=1, adain=True)
+    for a, b in zip(got2, ref2):
+        assert torch.equal(a, b)
