@@ -57,6 +57,10 @@ typedef struct pgt_epilogue {
   int32_t out_dtype;     /* PGT_BF16 / PGT_F32                                             */
   int32_t out_layout;    /* PGT_OUT_NHWC / PGT_OUT_NCHW                                    */
   int32_t flags;         /* PGT_EPI_FLAG_*                                                  */
+  float* gn_stats;       /* optional fp32 [rows/128, 4, 32, 2]: per-(tile, 32-row quadrant) (sum, sumsq) of the output per GroupNorm(32)
+                          * group, produced by the epilogue for the NEXT Normalize() (bf16 NHWC output, N % 32 == 0,
+                          * every 128-row tile inside one frame: pgt_conv_tiles_per_frame() > 0, or HW % 128 == 0 for
+                          * pgt_linear_bf16); consumed by pgt_groupnorm_apply_stats                         */
 } pgt_epilogue;
 
 const char* pgt_strerror(int status);
@@ -119,6 +123,13 @@ int pgt_conv_in_rgb(const float* x_nchw, int F, int H, int W, const float* w, co
  * Replaces Normalize()+nonlinearity (modules/rstt_layers.py:754-758,880-881,889-890) and
  * normalize()+swish (archs/pgtformer_arch.py:406-407,423-428). */
 int64_t pgt_groupnorm_ws_floats(int F, int HW, int C);
+/* tiles per frame of the conv launch (0 = tiles may span frames: no fused statistics for that shape) */
+int pgt_conv_tiles_per_frame(int Hin, int Win, int Cout, int ksize, int stride, int pad_lo);
+/* finalize + apply only, with the statistics already produced by the previous conv / linear epilogue
+ * (stats: [F, chunks_per_frame, 32, 2], chunks_per_frame = 4 x tiles per frame); saves the statistics pass over the tensor (1/3 of the GroupNorm traffic) */
+int pgt_groupnorm_apply_stats(const void* x, int ldx, int F, int HW, int C, const float* gamma, const float* beta,
+                              float eps, int apply_silu, void* y, int ldy, const float* stats, int chunks_per_frame,
+                              float* ws, void* stream);
 int pgt_groupnorm_silu(const void* x, int ldx, int F, int HW, int C, const float* gamma, const float* beta,
                        float eps, int apply_silu, void* y, int ldy, float* ws, void* stream);
 

@@ -20,7 +20,7 @@ class Epilogue(Structure):
     _fields_ = [('bias', c_void_p), ('act', c_int32), ('mode', c_int32), ('residual', c_void_p),
                 ('ldr', c_int32), ('res_dtype', c_int32), ('aux', c_void_p), ('ldaux', c_int32),
                 ('sft_w', c_float), ('out', c_void_p), ('ldo', c_int32), ('out_dtype', c_int32),
-                ('out_layout', c_int32), ('flags', c_int32)]
+                ('out_layout', c_int32), ('flags', c_int32), ('gn_stats', c_void_p)]
 
 
 # name -> (restype, argtypes); mirrors include/pgt_b200.h one to one
@@ -40,6 +40,9 @@ SIGNATURES = {
                                    POINTER(Epilogue), c_void_p]),
     'pgt_conv_in_rgb': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     'pgt_groupnorm_ws_floats': (c_int64, [c_int, c_int, c_int]),
+    'pgt_conv_tiles_per_frame': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    'pgt_groupnorm_apply_stats': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_int,
+                                          c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     'pgt_groupnorm_silu': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_int,
                                    c_void_p, c_int, c_void_p, c_void_p]),
     'pgt_layernorm': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int,

@@ -31,7 +31,7 @@ namespace pgt {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int EPI_WARPS = 8;
-constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32 + 32;     // TMA producer, MMA issuer, 8 epilogue warps, epilogue-DMA warp
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int PANEL_BYTES = BM * 128;            // one staging panel: 128 rows x 128 B
 constexpr int NUM_SLOTS = 4;                     // staging slots (two per epilogue half-group)
@@ -54,6 +54,8 @@ struct GemmParams {
   int has_res_map;       // fast path: residual is TMA-loaded through tmR
   const float* bias;
   int act, epi_mode;
+  float* gn_stats;       // optional: per-(tile, group) partial (sum, sumsq) of the OUTPUT for the next GroupNorm(32)
+  int gn_cpg;            // channels per group = N / 32
   int relu_after_res;    // ResNet BasicBlock: out = relu(conv + shortcut) — ReLU applied after the residual add
   const void* residual;
   int ldr, res_dtype;
@@ -70,10 +72,10 @@ struct GemmCfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGING_BYTES = NUM_SLOTS * PANEL_BYTES;
-  static constexpr int BUDGET = 232448 - 1024 /*align*/ - STAGING_BYTES - 2 * BN * 4 /*bias*/ - 256 /*barriers*/;
+  static constexpr int BUDGET = 232448 - 1024 /*align*/ - STAGING_BYTES - 2 * BN * 4 /*bias*/ - 1024 /*gn*/ - 256 /*barriers*/;
   static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 6 ? 6 : (BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 2 * BN * 4 + 256 + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 2 * BN * 4 + 1024 + 256 + 1024;
 };
 
 __device__ __forceinline__ void decode_conv_tile(const GemmParams& p, int m_blk, int& n0, int& y0, int& x0) {
@@ -116,29 +118,81 @@ __device__ __forceinline__ void act_chunk(float (&f)[32], int act) {
 // Shared by the GEMM/conv kernel and the halo-reuse conv kernel.  Runs on warps 2..9 (256 threads).
 struct EpiCtx {
   uint8_t* staging;        // NUM_SLOTS x PANEL_BYTES, 1024-aligned
-  float* bias_s;           // [2][BN]
   uint64_t* tmem_full;     // [2]
   uint64_t* tmem_empty;    // [2]
-  uint64_t* res_bar;       // [2]
+  uint64_t* res_bar;       // [NUM_SLOTS] staging slot prepared (free, residual landed)   DMA warp -> epilogue
+  uint64_t* slot_ready;    // [NUM_SLOTS] staging slot holds the finished panel           epilogue -> DMA warp
   uint32_t tmem_base;
 };
 
 // One 32-column chunk of a staging panel: TMEM -> +bias -> act -> (+residual | SFT) -> packed into the swizzled row.
+// Per-(quad, group) partial sums of one 32-column chunk for the fused GroupNorm statistics: each thread reduces
+// its row's channels per group (2G values: sum, sumsq), then the warp runs a reduce-scatter butterfly over its 32
+// rows — at every step a lane keeps one half of its values and ships the other half to its partner — so the whole
+// reduction costs ~2G shuffles instead of 10G; lane (or lane pair ..) i ends up owning value i.
+template <int CPG>
+__device__ __forceinline__ void gn_chunk_stats(const float (&f)[32], float* gq /*[32 groups][2] of this quad*/, int g0,
+                                               int lane) {
+  constexpr int G = 32 / CPG;
+  constexpr int NV = 2 * G;                    // interleaved (sum, sumsq) per group: value index = g*2 + which
+  float v[NV];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int e = 0; e < CPG; ++e) { const float x = f[g * CPG + e]; s += x; q = fmaf(x, x, q); }
+    v[2 * g] = s; v[2 * g + 1] = q;
+  }
+  int n = NV;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    if (n > 1) {
+      const int hlf = n >> 1;
+      const bool upper = (lane & o) != 0;
+#pragma unroll
+      for (int i = 0; i < NV / 2; ++i) {
+        if (i < hlf) {
+          const float keep = upper ? v[i + hlf] : v[i];
+          const float send = upper ? v[i] : v[i + hlf];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+      n = hlf;
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+    }
+  }
+  // value index owned by this lane: the lane bits consumed by the splitting steps (offsets 16, 8, ..)
+  constexpr int SPLIT = (NV >= 32) ? 5 : (NV >= 16) ? 4 : (NV >= 8) ? 3 : (NV >= 4) ? 2 : 1;
+  const int idx = lane >> (5 - SPLIT);
+  if ((lane & ((1 << (5 - SPLIT)) - 1)) == 0) gq[g0 * 2 + idx] = v[0];
+}
+
 template <bool kSft>
 __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, const float* bias32, uint8_t* srow,
-                                          int r, int sub, int esize, bool has_res) {
+                                          int r, int sub, int esize, bool has_res, float* gq = nullptr, int gcol = 0) {
   uint32_t v[32];
   tmem_ld_32x32(taddr, v);
   tmem_ld_wait();
   float f[32];
-  const float4* b4 = reinterpret_cast<const float4*>(bias32);
+  if (bias32 != nullptr) {                     // same address in every lane: an L1 broadcast read per float4
+    const float4* b4 = reinterpret_cast<const float4*>(bias32);
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 bb = b4[q];
-    f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + bb.x;
-    f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb.y;
-    f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb.z;
-    f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb.w;
+    for (int q = 0; q < 8; ++q) {
+      const float4 bb = __ldg(b4 + q);
+      f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + bb.x;
+      f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb.y;
+      f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb.z;
+      f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+    if (p.bias != nullptr) {                   // ragged N: guarded scalar reads
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (gcol + i < p.N) f[i] += __ldg(p.bias + gcol + i);
+    }
   }
   if (p.act != PGT_ACT_NONE && !p.relu_after_res) act_chunk(f, p.act);
   if (esize == 2) {
@@ -173,6 +227,16 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, c
       o.w = pack_bf16x2(f[8 * q + 6], f[8 * q + 7]);
       *dst = o;
     }
+    if (gq != nullptr) {                       // fused GroupNorm statistics of the (pre-rounding) output values
+      const int lane = r & 31;
+      switch (p.gn_cpg) {
+        case 2: gn_chunk_stats<2>(f, gq, 0, lane); break;
+        case 4: gn_chunk_stats<4>(f, gq, 0, lane); break;
+        case 8: gn_chunk_stats<8>(f, gq, 0, lane); break;
+        case 16: gn_chunk_stats<16>(f, gq, 0, lane); break;
+        default: gn_chunk_stats<32>(f, gq, 0, lane); break;
+      }
+    }
   } else {
     // 32 fp32 = 128 B = the whole swizzled row
 #pragma unroll
@@ -189,77 +253,112 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, c
   }
 }
 
-// Epilogue work is a stream of ITEMS = (tile, 128-byte-wide column panel), processed by all 8 epilogue warps
-// together (the two warps of a TMEM lane quadrant split the panel's 32-column chunks).  Items flow through a ring
-// of staging slots: the residual panel of item k+D is TMA-prefetched while item k is converted, and the TMA
-// store of item k drains while items k+1.. are processed, so neither latency sits on the critical path.
+// Epilogue work is a stream of ITEMS = (tile, 128-byte-wide column panel) flowing through a ring of staging slots.
+// Two roles:
+//   * 8 epilogue warps (two per TMEM lane quadrant, splitting a panel's 32-column chunks): wait until the slot is
+//     prepared, TMEM -> bias / activation / residual / SFT -> swizzled smem, signal `slot_ready`.  No CTA-level
+//     barrier and no serial bookkeeping sits on this path.
+//   * one DMA warp (epilogue_dma_loop): prepares slots ahead of time (waits for the previous TMA store out of the
+//     slot to drain, TMA-loads the residual / SFT-scale panel into it) and TMA-stores finished panels.
+struct ItemCursor {
+  int tile, pnl;
+};
+
 template <int BN>
-__device__ __forceinline__ void epilogue_loop(const GemmParams& p, const EpiCtx& ctx, const CUtensorMap& tmO,
-                                              const CUtensorMap& tmR, const CUtensorMap& tmX, int warp, int lane,
-                                              int num_tiles) {
-  uint8_t* staging = ctx.staging;
-  float* bias_s = ctx.bias_s;
+struct ItemStream {
+  const GemmParams& p;
+  int num_tiles, PW, panels_total;
+  __device__ ItemStream(const GemmParams& pp, int nt) : p(pp), num_tiles(nt) {
+    PW = 128 / (pp.out_dtype == PGT_BF16 ? 2 : 4);
+    panels_total = BN / PW;
+  }
+  __device__ int panels_in_tile(int t) const {       // panels whose first column is inside N
+    const int cb = (t % p.n_tiles) * BN;
+    const int n = (p.N - cb + PW - 1) / PW;
+    return n > panels_total ? panels_total : n;
+  }
+  __device__ bool valid(const ItemCursor& c) const { return c.tile < num_tiles; }
+  __device__ void next(ItemCursor& c) const {
+    if (++c.pnl >= panels_in_tile(c.tile)) { c.tile += gridDim.x; c.pnl = 0; }
+  }
+};
+
+template <int BN>
+__device__ __forceinline__ void epilogue_dma_loop(const GemmParams& p, const EpiCtx& ctx, const CUtensorMap& tmO,
+                                                  const CUtensorMap& tmR, const CUtensorMap& tmX, int lane, int num_tiles) {
+  if (!p.fast_epi) return;
+  const ItemStream<BN> is(p, num_tiles);
+  const bool sft = (p.epi_mode == PGT_EPI_SFT);
+  const int S = sft ? 2 : 1;                 // staging slots per item (SFT: residual/out + scale)
+  const int R = NUM_SLOTS / S;               // ring length in items
+  auto coords = [&](const ItemCursor& c, int& col, int& m_blk, int& n0, int& y0, int& x0) {
+    const int nb = c.tile % p.n_tiles;
+    m_blk = c.tile / p.n_tiles;
+    col = nb * BN + c.pnl * is.PW;
+    n0 = y0 = x0 = 0;
+    if (p.mode != MODE_LINEAR) decode_conv_tile(p, m_blk, n0, y0, x0);
+  };
+  // make ring position `pos` ready for item c: its residual (+scale) panel lands there, or it is simply declared free
+  auto prepare = [&](const ItemCursor& c, int pos) {
+    uint64_t* bar = &ctx.res_bar[pos];
+    if (!p.has_res_map) { mbar_arrive(bar); return; }
+    int col, m_blk, n0, y0, x0;
+    coords(c, col, m_blk, n0, y0, x0);
+    uint8_t* dst = ctx.staging + pos * S * PANEL_BYTES;
+    mbar_arrive_expect_tx(bar, S * PANEL_BYTES);
+    if (p.mode == MODE_LINEAR) {
+      tma_load_2d(dst, &tmR, bar, col, m_blk * BM);
+      if (sft) tma_load_2d(dst + PANEL_BYTES, &tmX, bar, col, m_blk * BM);
+    } else {
+      tma_load_4d(dst, &tmR, bar, col, x0, y0, n0);
+      if (sft) tma_load_4d(dst + PANEL_BYTES, &tmX, bar, col, x0, y0, n0);
+    }
+  };
+  ItemCursor cp{(int)blockIdx.x, 0}, cs{(int)blockIdx.x, 0};
+  if (lane == 0) {
+    for (int i = 0; i < R && is.valid(cp); ++i) { prepare(cp, i); is.next(cp); }
+  }
+  __syncwarp();
+  for (int k = 0; is.valid(cs); ++k, is.next(cs)) {
+    const int pos = k % R;
+    mbar_wait(&ctx.slot_ready[pos], (k / R) & 1);       // the 8 epilogue warps have written item k
+    if (lane == 0) {
+      int col, m_blk, n0, y0, x0;
+      coords(cs, col, m_blk, n0, y0, x0);
+      const uint8_t* src = ctx.staging + pos * S * PANEL_BYTES;
+      if (p.mode == MODE_LINEAR) tma_store_2d(&tmO, src, col, m_blk * BM);
+      else tma_store_4d(&tmO, src, col, x0, y0, n0);
+      bulk_commit();
+      if (is.valid(cp)) {                               // the slot is recycled for item k+R once the store has read it
+        bulk_wait_read<0>();
+        prepare(cp, pos);
+        is.next(cp);
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) bulk_wait0();                           // all output bytes written before the CTA retires
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_loop(const GemmParams& p, const EpiCtx& ctx, int warp, int lane, int num_tiles) {
   uint64_t* tmem_full = ctx.tmem_full;
   uint64_t* tmem_empty = ctx.tmem_empty;
-  uint64_t* res_bar = ctx.res_bar;             // [NUM_SLOTS]
   const uint32_t tmem_base = ctx.tmem_base;
   const int ew = warp - 2;                   // 0..7
   const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
   const int half = ew >> 2;                  // which of the quadrant's two warps
   const int r = quad * 32 + lane;            // row of the 128-row tile
-  const int et = threadIdx.x - 64;           // 0..255
-  const bool leader = (et == 0);
   const int esize = (p.out_dtype == PGT_BF16) ? 2 : 4;
-  const int PW = 128 / esize;                // columns per staging panel
+  const ItemStream<BN> is(p, num_tiles);
+  const int PW = is.PW;
   const int nsub = PW / 32;
-  const int panels_total = BN / PW;
   const bool sft = (p.epi_mode == PGT_EPI_SFT);
-  const int S = sft ? 2 : 1;                 // staging slots per item (SFT: residual/out + scale)
-  const int R = NUM_SLOTS / S;               // ring length in items
-  const int D = R / 2;                       // residual prefetch distance in items
-
-  // number of panels of tile `t` whose first column is inside N
-  auto panels_in_tile = [&](int t) {
-    const int cb = (t % p.n_tiles) * BN;
-    int n = (p.N - cb + PW - 1) / PW;
-    return n > panels_total ? panels_total : n;
-  };
-  // leader only: TMA-load the residual (and SFT scale) panel of item (t, pnl) into ring position `pos`
-  auto issue_res_load = [&](int t, int pnl, int pos) {
-    const int nb = t % p.n_tiles, mb = t / p.n_tiles;
-    const int c = nb * BN + pnl * PW;
-    uint8_t* dst = staging + pos * S * PANEL_BYTES;
-    uint64_t* bar = &res_bar[pos];
-    mbar_arrive_expect_tx(bar, S * PANEL_BYTES);
-    if (p.mode == MODE_LINEAR) {
-      tma_load_2d(dst, &tmR, bar, c, mb * BM);
-      if (sft) tma_load_2d(dst + PANEL_BYTES, &tmX, bar, c, mb * BM);
-    } else {
-      int n0, y0, x0;
-      decode_conv_tile(p, mb, n0, y0, x0);
-      tma_load_4d(dst, &tmR, bar, c, x0, y0, n0);
-      if (sft) tma_load_4d(dst + PANEL_BYTES, &tmX, bar, c, x0, y0, n0);
-    }
-  };
-  // advance (t, pnl) by `n` items in this CTA's item stream; false when the stream ends first
-  auto advance = [&](int& t, int& pnl, int n) -> bool {
-    while (n > 0) {
-      if (t >= num_tiles) return false;
-      ++pnl;
-      if (pnl >= panels_in_tile(t)) { t += gridDim.x; pnl = 0; }
-      --n;
-    }
-    return t < num_tiles;
-  };
+  const int S = sft ? 2 : 1;
+  const int R = NUM_SLOTS / S;
+  const bool bias_vec = p.bias != nullptr && (p.N % 32) == 0;   // whole chunks inside N: 128-bit bias reads
 
   int k = 0;                                 // item counter
-  if (p.fast_epi && p.has_res_map && leader) {
-    int t = blockIdx.x, pnl = 0;
-    for (int d = 0; d < D && t < num_tiles; ++d) {
-      issue_res_load(t, pnl, d % R);
-      if (!advance(t, pnl, 1)) break;
-    }
-  }
   int it = 0;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
     const int acc = it & 1;
@@ -268,42 +367,28 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, const EpiCtx&
     const int m_blk = tile / p.n_tiles;
     const int col_base = n_blk * BN;
     int n0 = 0, y0 = 0, x0 = 0;
-    if (p.mode != MODE_LINEAR) decode_conv_tile(p, m_blk, n0, y0, x0);
-    // bias slice of this tile -> smem (double-buffered by tile parity), one 256-thread barrier
-    float* bs = bias_s + (it & 1) * BN;
-    if (et < BN) bs[et] = (p.bias != nullptr && col_base + et < p.N) ? __ldg(p.bias + col_base + et) : 0.f;
-    named_bar_sync(3, EPI_WARPS * 32);
+    if (p.mode != MODE_LINEAR && !p.fast_epi) decode_conv_tile(p, m_blk, n0, y0, x0);
     const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
+    mbar_wait(&tmem_full[acc], acc_phase);
+    tc_fence_after();
 
     if (p.fast_epi) {
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const int npan = panels_in_tile(tile);
+      const int npan = is.panels_in_tile(tile);
       for (int pnl = 0; pnl < npan; ++pnl, ++k) {
         const int pos = k % R;
-        if (leader) {
-          // ring position of item k+D was last used by item k+D-R: all but the newest D-1 stores must have been read
-          if (D == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
-          if (p.has_res_map) {
-            int nt = tile, npnl = pnl;
-            if (advance(nt, npnl, D)) issue_res_load(nt, npnl, (k + D) % R);
-          }
-        }
-        if (p.has_res_map) mbar_wait(&res_bar[pos], (k / R) & 1);
-        uint8_t* srow = staging + pos * S * PANEL_BYTES + r * 128;
+        mbar_wait(&ctx.res_bar[pos], (k / R) & 1);      // slot free (and residual / scale panel landed)
+        uint8_t* srow = ctx.staging + pos * S * PANEL_BYTES + r * 128;
         const int pcol = pnl * PW;
         for (int sub = half; sub < nsub; sub += 2) {
-          if (sft) epi_chunk<true>(p, t_row + pcol + sub * 32, bs + pcol + sub * 32, srow, r, sub, esize, true);
-          else epi_chunk<false>(p, t_row + pcol + sub * 32, bs + pcol + sub * 32, srow, r, sub, esize, p.has_res_map != 0);
+          const int col0 = col_base + pcol + sub * 32;
+          const float* b32 = bias_vec ? p.bias + col0 : nullptr;
+          float* gq = nullptr;
+          if (p.gn_stats != nullptr) gq = p.gn_stats + (((size_t)m_blk * 4 + quad) * 32 + col0 / p.gn_cpg) * 2;
+          if (sft) epi_chunk<true>(p, t_row + pcol + sub * 32, b32, srow, r, sub, esize, true, gq, col0);
+          else epi_chunk<false>(p, t_row + pcol + sub * 32, b32, srow, r, sub, esize, p.has_res_map != 0, gq, col0);
         }
         fence_proxy_async();                 // generic smem writes -> visible to the TMA engine
-        named_bar_sync(4, EPI_WARPS * 32);   // item complete (also orders ring reuse R items later)
-        if (leader) {
-          const int c = col_base + pcol;
-          if (p.mode == MODE_LINEAR) tma_store_2d(&tmO, staging + pos * S * PANEL_BYTES, c, m_blk * BM);
-          else tma_store_4d(&tmO, staging + pos * S * PANEL_BYTES, c, x0, y0, n0);
-          bulk_commit();
-        }
+        mbar_arrive(&ctx.slot_ready[pos]);
       }
     } else {
       // ---------------- direct path (NCHW fp32 output, unaligned views, mixed residual dtype): per-thread global I/O
@@ -322,8 +407,6 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, const EpiCtx&
         valid = (pn < p.F) && (py < p.H) && (px < p.W);
         orow = ((long long)pn * p.H + py) * p.W + px;
       }
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
       const int c_lo = half * (BN / 2), c_hi = c_lo + BN / 2;
 #pragma unroll 1
       for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
@@ -336,7 +419,7 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, const EpiCtx&
           const int ncol = min(32, p.N - col0);
           float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bs[c0 + j];
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + ((p.bias != nullptr && j < ncol) ? __ldg(p.bias + col0 + j) : 0.f);
           if (p.act != PGT_ACT_NONE && !p.relu_after_res) act_chunk(f, p.act);
           if (p.residual != nullptr) {
             if (p.res_dtype == PGT_BF16) {
@@ -398,7 +481,6 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, const EpiCtx&
     tc_fence_before();
     mbar_arrive(&tmem_empty[acc]);
   }
-  if (p.fast_epi && leader) bulk_wait0();      // all output bytes written before the CTA retires
 }
 
 template <int BN>
@@ -413,14 +495,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;                 // 1024-aligned (all stage sizes are)
-  float* bias_s = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES);   // [2][BN]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 2 * BN);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
-  uint64_t* res_bar = bars + 2 * STAGES + 4;                           // [2 half-groups][2 slots]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
+  uint64_t* res_bar = bars + 2 * STAGES + 4;                           // [NUM_SLOTS]
+  uint64_t* slot_ready = bars + 2 * STAGES + 8;                        // [NUM_SLOTS]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 12);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -439,8 +521,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], EPI_WARPS * 32);
-      mbar_init(&res_bar[2 * i], 1);             // res_bar[NUM_SLOTS]: one per staging ring position
+      mbar_init(&res_bar[2 * i], 1);             // res_bar / slot_ready [NUM_SLOTS]: one per staging ring position
       mbar_init(&res_bar[2 * i + 1], 1);
+      mbar_init(&slot_ready[2 * i], EPI_WARPS * 32);
+      mbar_init(&slot_ready[2 * i + 1], EPI_WARPS * 32);
     }
     fence_barrier_init();
   }
@@ -526,10 +610,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else {
+  } else if (warp < 2 + EPI_WARPS) {
     // ------------------------------------------------------------------ epilogue (warps 2..9)
-    EpiCtx ctx{staging, bias_s, tmem_full, tmem_empty, res_bar, tmem_base};
-    epilogue_loop<BN>(p, ctx, tmO, tmR, tmX, warp, lane, num_tiles);
+    EpiCtx ctx{staging, tmem_full, tmem_empty, res_bar, slot_ready, tmem_base};
+    epilogue_loop<BN>(p, ctx, warp, lane, num_tiles);
+  } else {
+    // ------------------------------------------------------------------ epilogue DMA warp
+    EpiCtx ctx{staging, tmem_full, tmem_empty, res_bar, slot_ready, tmem_base};
+    epilogue_dma_loop<BN>(p, ctx, tmO, tmR, tmX, lane, num_tiles);
   }
 
   tc_fence_before();
@@ -543,22 +631,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // ------------------------------------------------------------------------------------------- halo-reuse conv
 // 3x3 stride-1 convolution for narrow outputs (Cout <= 128), where the plain implicit GEMM is bound by
-// L2 -> SM traffic (every tap re-reads its 128x64 A tile: 9x input traffic).  Here the 128-pixel tile is an
-// 8 x 16 patch and, per (dx, 64-channel block), ONE (8+2) x 16 halo slab is loaded; the three dy taps are the
-// same slab viewed at row offsets 0 / 16 / 32 (2048-byte steps, so the 128B-swizzle phase is unchanged and plain
-// UMMA descriptors apply).  A traffic drops from 9 to 3.75 tile-loads per channel block; the weights stream
-// through their own, deeper ring (one BN x 64 block per tap).
-constexpr int HALO_TW = 16, HALO_TH = 8;
-constexpr int HALO_A_BYTES = (HALO_TH + 2) * HALO_TW * 128;
+// L2 -> SM traffic (every tap re-reads its 128x64 A tile: 9x input traffic).  Here the 128-pixel tile is a
+// 16-row x 8-pixel patch and ONE (16+2) x (8+2) halo slab per 64-channel block serves all nine taps: tap (dy,dx)
+// is the same slab viewed from row offset dy*10+dx.  This relies on a property of the sm_100 UMMA shared-memory
+// descriptor measured with tools/probe/umma_shift_probe.cu: with SWIZZLE_128B the XOR phase is taken from the
+// absolute smem address, so a K-major operand may start at ANY 128-byte row of a TMA-written slab (base_offset 0)
+// and its 8-row groups may be any constant stride apart (SBO = slab pitch 1280 B, one image row of 10 pixels).
+// A traffic drops from 9 to 1.4 tile-loads per channel block; weights stream through their own ring, or stay
+// resident for the whole CTA when all nine taps fit (Cin = 64, Cout <= 64).
+constexpr int HALO_TW = 8, HALO_TH = 16;
+constexpr int HALO_PITCH = (HALO_TW + 2) * 128;                     // bytes between image rows of the slab
+constexpr int HALO_A_BYTES = (HALO_TH + 2) * HALO_PITCH;            // 23040
+constexpr int HALO_A_STRIDE = ((HALO_A_BYTES + 1023) / 1024) * 1024; // 23552: keep every slab 1024-aligned
+
+__device__ __forceinline__ uint64_t umma_desc_k_sw128_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 
 template <int BN>
 struct HaloCfg {
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int A_STAGES = (BN == 64) ? 4 : 3;
+  static constexpr int A_STAGES = (BN == 64) ? 3 : 2;
   static constexpr int B_STAGES = (BN == 64) ? 9 : 6;
   static constexpr int STAGING_BYTES = NUM_SLOTS * PANEL_BYTES;
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : 256;
-  static constexpr int SMEM_BYTES = A_STAGES * HALO_A_BYTES + B_STAGES * B_BYTES + STAGING_BYTES + 2 * BN * 4 + 512 + 1024;
+  static constexpr int SMEM_BYTES = A_STAGES * HALO_A_STRIDE + B_STAGES * B_BYTES + STAGING_BYTES + 2 * BN * 4 + 1024 + 512 + 1024;
   static_assert(SMEM_BYTES <= 232448, "halo conv smem budget");
 };
 
@@ -572,18 +674,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + AS * HALO_A_BYTES;
+  uint8_t* smem_b = smem + AS * HALO_A_STRIDE;
   uint8_t* staging = smem_b + BS * Cfg::B_BYTES;
-  float* bias_s = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 2 * BN);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + AS;
   uint64_t* b_full = bars + 2 * AS;
   uint64_t* b_empty = bars + 2 * AS + BS;
   uint64_t* tmem_full = bars + 2 * AS + 2 * BS;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_bar = tmem_full + 4;                                   // [2 half-groups][2 slots]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 8);
+  uint64_t* res_bar = tmem_full + 4;                                   // [NUM_SLOTS]
+  uint64_t* slot_ready = tmem_full + 8;                                // [NUM_SLOTS]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 12);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -595,13 +697,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
     if (p.fast_epi) tma_prefetch_desc(&tmO);
     if (p.has_res_map) tma_prefetch_desc(&tmR);
+    if (p.fast_epi && p.epi_mode == PGT_EPI_SFT) tma_prefetch_desc(&tmX);
     for (int i = 0; i < AS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], EPI_WARPS * 32);
-      mbar_init(&res_bar[2 * i], 1);             // res_bar[NUM_SLOTS]: one per staging ring position
+      mbar_init(&res_bar[2 * i], 1);
       mbar_init(&res_bar[2 * i + 1], 1);
+      mbar_init(&slot_ready[2 * i], EPI_WARPS * 32);
+      mbar_init(&slot_ready[2 * i + 1], EPI_WARPS * 32);
     }
     fence_barrier_init();
   }
@@ -614,77 +719,76 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    {
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_blk = tile % p.n_tiles;
-        const int m_blk = tile / p.n_tiles;
-        int n0, y0, x0;
-        decode_conv_tile(p, m_blk, n0, y0, x0);
-        for (int cb = 0; cb < p.cin_blocks; ++cb) {
-          for (int dx = 0; dx < 3; ++dx) {
-            mbar_wait(&a_empty[as], aph ^ 1);
-            if (elect_one()) {
-              mbar_arrive_expect_tx(&a_full[as], HALO_A_BYTES);
-              tma_load_4d(smem_a + as * HALO_A_BYTES, &tmA, &a_full[as], cb * BK, x0 + dx - 1, y0 - 1, n0);
-            }
-            __syncwarp();
-            if (++as == AS) { as = 0; aph ^= 1; }
-            if (p.b_resident && tile != (int)blockIdx.x) continue;   // weights already resident in the ring
-            for (int dy = 0; dy < 3; ++dy) {
-              mbar_wait(&b_empty[bs], bph ^ 1);
-              if (elect_one()) {
-                mbar_arrive_expect_tx(&b_full[bs], Cfg::B_BYTES);
-                tma_load_2d(smem_b + bs * Cfg::B_BYTES, &tmB, &b_full[bs], (dy * 3 + dx) * cin_pad + cb * BK, n_blk * BN);
-              }
-              __syncwarp();
-              if (++bs == BS) { bs = 0; bph ^= 1; }
-            }
+    // ------------------------------------------------------------------ TMA producer
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.n_tiles;
+      const int m_blk = tile / p.n_tiles;
+      int n0, y0, x0;
+      decode_conv_tile(p, m_blk, n0, y0, x0);
+      for (int cb = 0; cb < p.cin_blocks; ++cb) {
+        mbar_wait(&a_empty[as], aph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&a_full[as], HALO_A_BYTES);
+          tma_load_4d(smem_a + as * HALO_A_STRIDE, &tmA, &a_full[as], cb * BK, x0 - 1, y0 - 1, n0);
+        }
+        __syncwarp();
+        if (++as == AS) { as = 0; aph ^= 1; }
+        if (p.b_resident && tile != (int)blockIdx.x) continue;   // weights already resident in the ring
+        for (int t = 0; t < 9; ++t) {
+          mbar_wait(&b_empty[bs], bph ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&b_full[bs], Cfg::B_BYTES);
+            tma_load_2d(smem_b + bs * Cfg::B_BYTES, &tmB, &b_full[bs], t * cin_pad + cb * BK, n_blk * BN);
           }
+          __syncwarp();
+          if (++bs == BS) { bs = 0; bph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        uint32_t accumulate = 0;
-        const int macros = 3 * p.cin_blocks;
-        for (int mc = 0; mc < macros; ++mc) {
-          mbar_wait(&a_full[as], aph);
-          const uint32_t a_addr = smem_u32(smem_a + as * HALO_A_BYTES);
-          for (int dy = 0; dy < 3; ++dy) {
-            if (!p.b_resident || it == 0) mbar_wait(&b_full[bs], bph);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t da = umma_desc_k_sw128(a_addr + dy * (HALO_TW * 128));
-              const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + bs * Cfg::B_BYTES));
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      uint32_t accumulate = 0;
+      for (int cb = 0; cb < p.cin_blocks; ++cb) {
+        mbar_wait(&a_full[as], aph);
+        const uint32_t a_addr = smem_u32(smem_a + as * HALO_A_STRIDE);
+        for (int t = 0; t < 9; ++t) {
+          if (!p.b_resident || it == 0) mbar_wait(&b_full[bs], bph);
+          tc_fence_after();
+          if (elect_one()) {
+            const int dy = t / 3, dx = t - 3 * dy;
+            const uint64_t da = umma_desc_k_sw128_sbo(a_addr + (dy * (HALO_TW + 2) + dx) * 128, HALO_PITCH);
+            const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + bs * Cfg::B_BYTES));
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (accumulate | k) != 0 ? 1u : 0u);
-              if (!p.b_resident) umma_commit(&b_empty[bs]);
-              if (dy == 2) umma_commit(&a_empty[as]);
-              if (dy == 2 && mc == macros - 1) umma_commit(&tmem_full[acc]);
-            }
-            __syncwarp();
-            accumulate = 1;
-            if (++bs == BS) { bs = 0; bph ^= 1; }
+            for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (accumulate | k) != 0 ? 1u : 0u);
+            if (!p.b_resident) umma_commit(&b_empty[bs]);
+            if (t == 8) umma_commit(&a_empty[as]);
+            if (t == 8 && cb == p.cin_blocks - 1) umma_commit(&tmem_full[acc]);
           }
-          if (++as == AS) { as = 0; aph ^= 1; }
+          __syncwarp();
+          accumulate = 1;
+          if (++bs == BS) { bs = 0; bph ^= 1; }
         }
+        if (++as == AS) { as = 0; aph ^= 1; }
       }
     }
+  } else if (warp < 2 + EPI_WARPS) {
+    EpiCtx ctx{staging, tmem_full, tmem_empty, res_bar, slot_ready, tmem_base};
+    epilogue_loop<BN>(p, ctx, warp, lane, num_tiles);
   } else {
-    EpiCtx ctx{staging, bias_s, tmem_full, tmem_empty, res_bar, tmem_base};
-    epilogue_loop<BN>(p, ctx, tmO, tmR, tmX, warp, lane, num_tiles);
+    EpiCtx ctx{staging, tmem_full, tmem_empty, res_bar, slot_ready, tmem_base};
+    epilogue_dma_loop<BN>(p, ctx, tmO, tmR, tmX, lane, num_tiles);
   }
 
   tc_fence_before();
@@ -765,6 +869,15 @@ static int setup_epilogue_maps(GemmParams& p, const CUtensorMap& placeholder, CU
     if (p.res_dtype == p.out_dtype && aligned16(p.residual) && ((long long)p.ldr * esize) % 16 == 0) p.has_res_map = 1;
     else p.fast_epi = 0;
   }
+  if (p.gn_stats != nullptr) {
+    // fused GroupNorm statistics live on the bf16 TMA-store path; every 128-row tile must sit inside one frame
+    const int cpg = p.N / 32;
+    const bool ok = p.fast_epi && p.out_dtype == PGT_BF16 && (p.N % 32) == 0 && p.o_sx == 0 &&
+                    (cpg == 2 || cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32) &&
+                    (p.mode == MODE_LINEAR || p.tn == 1);
+    if (!ok) return PGT_ERR_UNSUPPORTED;
+    p.gn_cpg = cpg;
+  }
   tmO = placeholder;
   tmR = placeholder;                               // placeholders when unused (never dereferenced)
   tmX = placeholder;
@@ -776,7 +889,7 @@ static int setup_epilogue_maps(GemmParams& p, const CUtensorMap& placeholder, CU
       if (rc != PGT_OK) return rc;
     }
     if (p.epi_mode == PGT_EPI_SFT) {
-      if (!p.has_res_map) { p.fast_epi = 0; return PGT_OK; }
+      if (!p.has_res_map) { p.fast_epi = 0; return p.gn_stats ? PGT_ERR_UNSUPPORTED : PGT_OK; }
       rc = encode_out_map(&tmX, p, p.aux, p.ldaux, PGT_BF16);
       if (rc != PGT_OK) return rc;
     }
@@ -882,6 +995,8 @@ static int fill_epilogue(GemmParams& p, const pgt_epilogue* ep) {
   p.out_dtype = ep->out_dtype;
   p.out_layout = ep->out_layout;
   p.relu_after_res = (ep->flags & PGT_EPI_FLAG_RELU_AFTER_RESIDUAL) ? 1 : 0;
+  p.gn_stats = ep->gn_stats;
+  p.gn_cpg = 0;
   if (p.relu_after_res && (p.act != PGT_ACT_RELU || p.epi_mode != PGT_EPI_PLAIN)) return PGT_ERR_INVALID;
   if (p.epi_mode == PGT_EPI_SFT && (p.residual == nullptr || p.aux == nullptr || p.res_dtype != PGT_BF16))
     return PGT_ERR_INVALID;
@@ -977,7 +1092,7 @@ static int conv_impl(const void* x, int F, int Hin, int Win, int Cin, int ldx, c
   if (p.mode == MODE_CONV_S1) {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)F};
     uint64_t str[3] = {(uint64_t)ldx * 2, (uint64_t)Win * ldx * 2, (uint64_t)Hin * Win * ldx * 2};
-    uint32_t box[4] = {BK, (uint32_t)tw, (uint32_t)(halo ? th + 2 : th), (uint32_t)tn};
+    uint32_t box[4] = {BK, (uint32_t)(halo ? tw + 2 : tw), (uint32_t)(halo ? th + 2 : th), (uint32_t)tn};
     rc = encode_map(&tmA, x, 4, dims, str, box);
     if (rc == PGT_OK && halo) {
       cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -997,6 +1112,22 @@ static int conv_impl(const void* x, int F, int Hin, int Win, int Cin, int ldx, c
     if (!aligned16(p.out) || ((long long)p.ldo * esz) % 16 != 0) return PGT_ERR_UNSUPPORTED;
   }
   return dispatch_gemm(tmA, Wp, ldw, p, static_cast<cudaStream_t>(stream));
+}
+
+// 128-row tiles per frame of the conv the library would launch for this shape (0: a tile may span frames, so the
+// fused GroupNorm statistics are unavailable).  Mirrors the tile selection of conv_impl.
+extern "C" int pgt_conv_tiles_per_frame(int Hin, int Win, int Cout, int ksize, int stride, int pad_lo) {
+  static const bool no_halo = getenv("PGT_NO_HALO") != nullptr;
+  const int H = Hin / stride, W = Win / stride;
+  const bool halo = !no_halo && stride == 1 && ksize == 3 && pad_lo == 1 && Cout <= 128 && Hin >= HALO_TH && Win >= HALO_TW;
+  int tw = 1, th = 1;
+  if (halo) { tw = HALO_TW; th = HALO_TH; }
+  else {
+    while (tw * 2 <= W && tw * 2 <= BM) tw *= 2;
+    while (th * 2 <= H && tw * th * 2 <= BM) th *= 2;
+  }
+  if (tw * th != BM) return 0;
+  return ceil_div(W, tw) * ceil_div(H, th);
 }
 
 extern "C" int pgt_conv_bf16(const void* x, int F, int Hin, int Win, int Cin, int ldx, const void* Wp, int ldw,

@@ -86,18 +86,39 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int HW, int C, int
 
 // Pass 2 (tiny): fold the chunk partials (fp64) into per-(frame, channel) affine terms
 // a = rstd*gamma, b = beta - mean*rstd*gamma, stored after the partials in the workspace.
-__global__ void __launch_bounds__(256)
+constexpr int GN_FIN_PARTS = 32;
+__global__ void __launch_bounds__(GN_FIN_PARTS * 32)
 gn_finalize_kernel(const float* __restrict__ partial, int nchunks, int HW, int C, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float eps, float* __restrict__ ab /*[F][2][C]*/) {
   __shared__ float smean[GN_GROUPS], srstd[GN_GROUPS];
+  __shared__ double ps[GN_FIN_PARTS][GN_GROUPS], pq[GN_FIN_PARTS][GN_GROUPS];
   const int f = blockIdx.x;
   const int cpg = C / GN_GROUPS;
+  {
+    // 32 threads per group stride over the chunks (fused-epilogue statistics come as thousands of per-tile rows;
+    // 4 independent loads in flight), then a fixed-order combine: deterministic
+    const int g = threadIdx.x & 31, part = threadIdx.x >> 5;
+    const float2* base = reinterpret_cast<const float2*>(partial) + (size_t)f * nchunks * GN_GROUPS + g;
+    double s = 0.0, q = 0.0;
+    int ch = part;
+    for (; ch + 3 * GN_FIN_PARTS < nchunks; ch += 4 * GN_FIN_PARTS) {
+      const float2 o0 = __ldg(base + (size_t)ch * GN_GROUPS);
+      const float2 o1 = __ldg(base + (size_t)(ch + GN_FIN_PARTS) * GN_GROUPS);
+      const float2 o2 = __ldg(base + (size_t)(ch + 2 * GN_FIN_PARTS) * GN_GROUPS);
+      const float2 o3 = __ldg(base + (size_t)(ch + 3 * GN_FIN_PARTS) * GN_GROUPS);
+      s += ((double)o0.x + (double)o1.x) + ((double)o2.x + (double)o3.x);
+      q += ((double)o0.y + (double)o1.y) + ((double)o2.y + (double)o3.y);
+    }
+    for (; ch < nchunks; ch += GN_FIN_PARTS) {
+      const float2 o = __ldg(base + (size_t)ch * GN_GROUPS);
+      s += (double)o.x; q += (double)o.y;
+    }
+    ps[part][g] = s; pq[part][g] = q;
+  }
+  __syncthreads();
   if (threadIdx.x < GN_GROUPS) {
     double s = 0.0, q = 0.0;
-    for (int ch = 0; ch < nchunks; ++ch) {
-      const float* o = partial + (((size_t)f * nchunks + ch) * GN_GROUPS + threadIdx.x) * 2;
-      s += (double)o[0]; q += (double)o[1];
-    }
+    for (int part = 0; part < GN_FIN_PARTS; ++part) { s += ps[part][threadIdx.x]; q += pq[part][threadIdx.x]; }
     const double n = (double)HW * cpg;
     const double mean = s / n;
     double var = q / n - mean * mean;
@@ -342,7 +363,7 @@ extern "C" int pgt_groupnorm_silu(const void* x, int ldx, int F, int HW, int C, 
   gn_stats_kernel<<<dim3(nchunks, F), GN_THREADS, stats_smem, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C, ppc, ws);
   PGT_LAUNCH_OK();
-  gn_finalize_kernel<<<F, 256, 0, st>>>(ws, nchunks, HW, C, gamma, beta, eps, ab);
+  gn_finalize_kernel<<<F, GN_FIN_PARTS * 32, 0, st>>>(ws, nchunks, HW, C, gamma, beta, eps, ab);
   PGT_LAUNCH_OK();
   // apply: ~128 KB of activations per block
   int ppb = (131072 / (C * 2));
@@ -351,6 +372,23 @@ extern "C" int pgt_groupnorm_silu(const void* x, int ldx, int F, int HW, int C, 
   gn_apply_kernel<<<dim3(nblk, F), GN_APPLY_THREADS, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C, ppb, ab, apply_silu,
       reinterpret_cast<__nv_bfloat16*>(y), ldy);
+  PGT_LAUNCH_OK();
+  return PGT_OK;
+}
+
+extern "C" int pgt_groupnorm_apply_stats(const void* x, int ldx, int F, int HW, int C, const float* gamma,
+                                         const float* beta, float eps, int apply_silu, void* y, int ldy,
+                                         const float* stats, int chunks_per_frame, float* ws, void* stream) {
+  PGT_CHECK_ARG(x && y && ws && gamma && beta && stats && F > 0 && HW > 0 && chunks_per_frame > 0);
+  PGT_CHECK_ARG(C % 32 == 0 && C % 8 == 0 && C / 8 <= GN_APPLY_THREADS && ldx % 8 == 0 && ldy % 8 == 0);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope ps(PGT_PROF_NORM, 2.0 * F * (double)HW * C * 2, st, "gn_apply_stats");   // read + write (bf16)
+  gn_finalize_kernel<<<F, GN_FIN_PARTS * 32, 0, st>>>(stats, chunks_per_frame, HW, C, gamma, beta, eps, ws);
+  PGT_LAUNCH_OK();
+  int ppb = (131072 / (C * 2));
+  if (ppb < 16) ppb = 16;
+  gn_apply_kernel<<<dim3(ceil_div(HW, ppb), F), GN_APPLY_THREADS, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C, ppb, ws, apply_silu, reinterpret_cast<__nv_bfloat16*>(y), ldy);
   PGT_LAUNCH_OK();
   return PGT_OK;
 }

@@ -114,30 +114,49 @@ class Engine:
     def _new(self, *shape, dtype=BF):
         return torch.empty(*shape, dtype=dtype, device=self.dev)
 
+    fuse_gn_stats = True      # GroupNorm statistics from the producing conv / linear epilogue (saves one pass)
+
     def _gn(self, x, p, silu=True):
+        gn = getattr(x, '_pgt_gn', None)
+        if gn is not None:
+            return ops.groupnorm_apply_stats(x, self.w[p + '.weight'], self.w[p + '.bias'], self._new(*x.shape), gn[0], gn[1],
+                                             silu=silu)
         return ops.groupnorm_silu(x, self.w[p + '.weight'], self.w[p + '.bias'], self._new(*x.shape), silu=silu)
 
-    def _conv3(self, x, p, cout, out=None, **kw):
+    def _conv3(self, x, p, cout, out=None, gn_out=False, **kw):
         Fr, H, W, _ = x.shape
         stride = kw.get('stride', 1)
         if out is None:
             out = self._new(Fr, H // stride, W // stride, cout)
-        return ops.conv(x, self.w[p + '.weight'], cout, out, bias=self.w.get(p + '.bias'), **kw)
+        stats = None
+        if gn_out and self.fuse_gn_stats and cout % 32 == 0 and cout // 32 in (2, 4, 8, 16, 32) and out.is_contiguous():
+            tpf = ops.conv_tiles_per_frame(H, W, cout, kw.get('ksize', 3), stride, kw.get('pad_lo', 1))
+            if tpf > 0:
+                stats = self._new(Fr * tpf * 4 * 64, dtype=torch.float32)      # [tile][TMEM quadrant][32 groups][2]
+                out._pgt_gn = (stats, tpf * 4)
+        return ops.conv(x, self.w[p + '.weight'], cout, out, bias=self.w.get(p + '.bias'), gn_stats=stats, **kw)
 
-    def _lin(self, x, p, n, out=None, out_dtype=BF, **kw):
+    def _lin(self, x, p, n, out=None, out_dtype=BF, gn_out=False, **kw):
         if out is None:
             out = self._new(*x.shape[:-1], n, dtype=out_dtype)
-        return ops.linear(x, self.w[p + '.weight'], out, bias=self.w.get(p + '.bias'), N=n, **kw)
+        stats = None
+        if gn_out and self.fuse_gn_stats and out.dim() == 4 and out.dtype == BF and n % 32 == 0 and \
+                n // 32 in (2, 4, 8, 16, 32) and (out.shape[1] * out.shape[2]) % 128 == 0 and out.is_contiguous():
+            tpf = out.shape[1] * out.shape[2] // 128
+            stats = self._new(out.shape[0] * tpf * 4 * 64, dtype=torch.float32)
+            out._pgt_gn = (stats, tpf * 4)
+        return ops.linear(x, self.w[p + '.weight'], out, bias=self.w.get(p + '.bias'), N=n, gn_stats=stats, **kw)
 
     # ------------------------------------------------------------------ blocks
-    def td_resblock(self, x, p, cout):
+    def td_resblock(self, x, p, cout, gn_next=False):
         """TDResnetBlock (`modules/rstt_layers.py:875-904`): 2 x (GN+SiLU -> conv3x3), residual in the
-        second conv's epilogue (1x1 nin_shortcut first when the width changes)."""
-        h = self._conv3(self._gn(x, p + '.norm1'), p + '.conv1', cout)
+        second conv's epilogue (1x1 nin_shortcut first when the width changes).  conv1's epilogue also emits the
+        GroupNorm statistics norm2 needs; with gn_next the block output carries them for the next Normalize()."""
+        h = self._conv3(self._gn(x, p + '.norm1'), p + '.conv1', cout, gn_out=True)
         sc = self._lin(x, p + '.nin_shortcut', cout) if (p + '.nin_shortcut.weight') in self.w else x
-        return self._conv3(self._gn(h, p + '.norm2'), p + '.conv2', cout, residual=sc)
+        return self._conv3(self._gn(h, p + '.norm2'), p + '.conv2', cout, residual=sc, gn_out=gn_next)
 
-    def swin_block(self, x, p, heads, shift):
+    def swin_block(self, x, p, heads, shift, gn_next=False):
         """VSTSREncoderTransformerBlock (`modules/rstt_layers.py:284-338`) on [F,H,W,C]."""
         Fr, H, W, C = x.shape
         w = self.w
@@ -147,14 +166,15 @@ class Engine:
         x = self._lin(a, p + '.attn.proj', C, residual=x)
         y = ops.layernorm(x, w[p + '.norm2.weight'], w[p + '.norm2.bias'], self._new(Fr, H, W, C))
         m = self._lin(y, p + '.mlp.fc1', C, act=ops.ACT_GELU)
-        return self._lin(m, p + '.mlp.fc2', C, residual=x)
+        return self._lin(m, p + '.mlp.fc2', C, residual=x, gn_out=gn_next)
 
-    def encoder_layer(self, x, p, heads, depth):
+    def encoder_layer(self, x, p, heads, depth, gn_next=False):
         for i in range(depth):
-            x = self.swin_block(x, '%s.blocks.%d' % (p, i), heads, 2 if i % 2 == 1 else 0)
+            x = self.swin_block(x, '%s.blocks.%d' % (p, i), heads, 2 if i % 2 == 1 else 0,
+                                gn_next=gn_next and i == depth - 1)
         return x
 
-    def fuse_sft(self, enc, dec, key, wgt):
+    def fuse_sft(self, enc, dec, key, wgt, gn_next=False):
         """Fuse_sft_block (`archs/pgtformer_arch.py:460-484`); the final
         dec + w*(dec*scale + shift) is the epilogue of the last `shift` conv."""
         p = 'fuse_convs_dict.' + key
@@ -169,12 +189,12 @@ class Engine:
         fut = ops.regroup_frames(self._lin(tcat, p + '.tfusion0', 96), self._new(Fr, P, 32), b, P, 32, 1)
         self._lin(fut, p + '.tfusion1', 32, out=cat.view(Fr, P, 2 * C + 32)[..., 2 * C:])
         e = p + '.encode_enc'
-        h = self._conv3(self._gn(cat, e + '.norm1'), e + '.conv1', C)
+        h = self._conv3(self._gn(cat, e + '.norm1'), e + '.conv1', C, gn_out=True)
         sc = self._lin(cat, e + '.conv_out', C)
         ef = self._conv3(self._gn(h, e + '.norm2'), e + '.conv2', C, residual=sc)
         scale = self._conv3(self._conv3(ef, p + '.scale.0', C, act=ops.ACT_LRELU02), p + '.scale.2', C)
         sh = self._conv3(ef, p + '.shift.0', C, act=ops.ACT_LRELU02)
-        return self._conv3(sh, p + '.shift.2', C, residual=dec, sft_scale=scale, sft_w=wgt)
+        return self._conv3(sh, p + '.shift.2', C, residual=dec, sft_scale=scale, sft_w=wgt, gn_out=gn_next)
 
     # ------------------------------------------------------------------ parsing net (BiSeNet / ResNet18)
     def _repack_parsing(self):
@@ -294,16 +314,22 @@ class Engine:
         h = ops.conv_in_rgb(x, self.w['encoder.conv_in.weight'], self.w['encoder.conv_in.bias'], self._new(Fr, H, W, a.ch))
         feats = []
         for lvl in range(a.num_levels):
+            last = lvl == a.num_levels - 1
             for blk in range(a.num_res_blocks):
-                h = self.td_resblock(h, 'encoder.down.%d.block.%d' % (lvl, blk), a.level_ch[lvl])
+                # the next consumer of this level's output is a Normalize() only at the last level (mid.block_1);
+                # otherwise it is the stride-2 Downsample conv, whose own epilogue feeds the next level's norm1
+                nxt = last and blk == a.num_res_blocks - 1
+                h = self.td_resblock(h, 'encoder.down.%d.block.%d' % (lvl, blk), a.level_ch[lvl],
+                                     gn_next=nxt and not a.level_has_attn[lvl])
                 if a.level_has_attn[lvl]:
-                    h = self.encoder_layer(h, 'encoder.down.%d.attn.%d' % (lvl, blk), a.num_heads[lvl], a.depths[lvl])
+                    h = self.encoder_layer(h, 'encoder.down.%d.attn.%d' % (lvl, blk), a.num_heads[lvl], a.depths[lvl],
+                                           gn_next=nxt)
             feats.append(h)
-            if lvl != a.num_levels - 1:
-                h = self._conv3(h, 'encoder.down.%d.downsample.conv' % lvl, a.level_ch[lvl], stride=2, pad_lo=0)
+            if not last:
+                h = self._conv3(h, 'encoder.down.%d.downsample.conv' % lvl, a.level_ch[lvl], stride=2, pad_lo=0, gn_out=True)
         h = self.td_resblock(h, 'encoder.mid.block_1', a.level_ch[-1])
-        h = self.encoder_layer(h, 'encoder.mid.attn_1', a.num_heads[-1], a.depths[-1])
-        h = self.td_resblock(h, 'encoder.mid.block_2', a.level_ch[-1])
+        h = self.encoder_layer(h, 'encoder.mid.attn_1', a.num_heads[-1], a.depths[-1], gn_next=True)
+        h = self.td_resblock(h, 'encoder.mid.block_2', a.level_ch[-1], gn_next=True)
         zc = 2 * a.z_channels if a.double_z else a.z_channels
         return self._conv3(self._gn(h, 'encoder.norm_out'), 'encoder.conv_out', zc), feats
 
@@ -311,17 +337,24 @@ class Engine:
         """Decoder.forward (`archs/tdcrqvae3_arch.py:672-707`) / the inlined variant with SFT fusion
         (`archs/pgtformer_arch.py:680-710`).  z: [F,h,w,z_channels] bf16 -> out fp32 NCHW."""
         a = self.arch
-        h = self._conv3(z, 'decoder.conv_in', a.level_ch[-1])
+        h = self._conv3(z, 'decoder.conv_in', a.level_ch[-1], gn_out=True)
         h = self.td_resblock(h, 'decoder.mid.block_1', a.level_ch[-1])
-        h = self.encoder_layer(h, 'decoder.mid.attn_1', a.num_heads[-1], a.depths[-1])
-        h = self.td_resblock(h, 'decoder.mid.block_2', a.level_ch[-1])
+        h = self.encoder_layer(h, 'decoder.mid.attn_1', a.num_heads[-1], a.depths[-1], gn_next=True)
+        h = self.td_resblock(h, 'decoder.mid.block_2', a.level_ch[-1], gn_next=True)
         for lvl in reversed(range(a.num_levels)):
-            for blk in range(a.num_res_blocks + 1):
-                h = self.td_resblock(h, 'decoder.up.%d.block.%d' % (lvl, blk), a.level_ch[lvl])
+            nblk = a.num_res_blocks + 1
+            fuse = feats is not None and lvl in a.fuse_level_key and wgt > 0
+            for blk in range(nblk):
+                # next consumer is a Normalize(): the next block of this level, or decoder.norm_out after the very
+                # last block; after the level's last block comes the SFT concat / the upsample conv instead
+                nxt = blk < nblk - 1 or (lvl == 0 and not fuse)
+                h = self.td_resblock(h, 'decoder.up.%d.block.%d' % (lvl, blk), a.level_ch[lvl],
+                                     gn_next=nxt and not a.level_has_attn[lvl])
                 if a.level_has_attn[lvl]:
-                    h = self.encoder_layer(h, 'decoder.up.%d.attn.%d' % (lvl, blk), a.num_heads[lvl], a.depths[lvl])
-            if feats is not None and lvl in a.fuse_level_key and wgt > 0:
-                h = self.fuse_sft(feats[lvl], h, a.fuse_level_key[lvl], wgt)
+                    h = self.encoder_layer(h, 'decoder.up.%d.attn.%d' % (lvl, blk), a.num_heads[lvl], a.depths[lvl],
+                                           gn_next=nxt)
+            if fuse:
+                h = self.fuse_sft(feats[lvl], h, a.fuse_level_key[lvl], wgt, gn_next=(lvl == 0))
             if lvl != 0:
                 Fr, H, W, C = h.shape
                 p = 'decoder.up.%d.upsample.conv' % lvl

@@ -44,9 +44,12 @@ def _rows(t):
 
 
 def make_epilogue(out, bias=None, act=ACT_NONE, residual=None, sft_scale=None, sft_w=0.0, nchw=False,
-                  relu_after_res=False):
+                  relu_after_res=False, gn_stats=None):
     ep = Epilogue()
     ep.flags = 1 if relu_after_res else 0
+    if gn_stats is not None:
+        assert gn_stats.dtype == torch.float32 and gn_stats.is_contiguous()
+        ep.gn_stats = gn_stats.data_ptr()
     ep.bias = bias.data_ptr() if bias is not None else None
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous()
@@ -69,7 +72,7 @@ def make_epilogue(out, bias=None, act=ACT_NONE, residual=None, sft_scale=None, s
     return ep
 
 
-def linear(a, w, out, bias=None, act=ACT_NONE, residual=None, K=None, N=None, relu_after_res=False):
+def linear(a, w, out, bias=None, act=ACT_NONE, residual=None, K=None, N=None, relu_after_res=False, gn_stats=None):
     """out[T,N] = act(a[T,K] @ w[N,K]^T + bias) (+ residual).  a, w bf16; out bf16 / fp32."""
     lib = L.load()
     M, Ka, lda = _rows(a)
@@ -78,19 +81,19 @@ def linear(a, w, out, bias=None, act=ACT_NONE, residual=None, K=None, N=None, re
     N = N if N is not None else Nw
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.stride(1) == 1
     assert _rows(out)[0] == M and out.shape[-1] >= N
-    ep = make_epilogue(out, bias, act, residual, relu_after_res=relu_after_res)
+    ep = make_epilogue(out, bias, act, residual, relu_after_res=relu_after_res, gn_stats=gn_stats)
     L.check(lib.pgt_linear_bf16(_p(a), lda, _p(w), w.stride(0), M, N, K, ctypes.byref(ep), _stream()))
     return out
 
 
 def conv(x, wp, cout, out, ksize=3, stride=1, pad_lo=1, bias=None, act=ACT_NONE, residual=None, sft_scale=None,
-         sft_w=0.0, nchw=False, relu_after_res=False):
+         sft_w=0.0, nchw=False, relu_after_res=False, gn_stats=None):
     """Implicit-GEMM conv on [F,H,W,Cin] bf16 with packed weights wp [>=cout, k*k*CinPad]."""
     lib = L.load()
     F, H, W, Cin = x.shape
     assert x.dtype == torch.bfloat16 and x.stride(3) == 1 and x.stride(1) == W * x.stride(2) and \
         (F == 1 or x.stride(0) == H * x.stride(1))
-    ep = make_epilogue(out, bias, act, residual, sft_scale, sft_w, nchw, relu_after_res)
+    ep = make_epilogue(out, bias, act, residual, sft_scale, sft_w, nchw, relu_after_res, gn_stats)
     L.check(lib.pgt_conv_bf16(_p(x), F, H, W, Cin, x.stride(2), _p(wp), wp.stride(0), cout, ksize, stride, pad_lo,
                               ctypes.byref(ep), _stream()))
     return out
@@ -135,6 +138,26 @@ def groupnorm_silu(x, gamma, beta, out, eps=1e-6, silu=True):
         _gn_ws[key] = ws
     L.check(lib.pgt_groupnorm_silu(_p(x), ldx, F, HW, C, _p(gamma), _p(beta), eps, int(silu), _p(out), ldy, _p(ws),
                                    _stream()))
+    return out
+
+
+def conv_tiles_per_frame(H, W, cout, ksize=3, stride=1, pad_lo=1):
+    return int(L.load().pgt_conv_tiles_per_frame(H, W, cout, ksize, stride, pad_lo))
+
+
+def groupnorm_apply_stats(x, gamma, beta, out, stats, chunks_per_frame, eps=1e-6, silu=True):
+    """GroupNorm(32)+SiLU whose statistics were produced by the previous conv / linear epilogue."""
+    lib = L.load()
+    F = x.shape[0]
+    C = x.shape[-1]
+    HW = x.shape[1] * x.shape[2]
+    key = ('ab', x.device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _gn_ws.get(key)
+    if ws is None or ws.numel() < F * 2 * C:
+        ws = torch.empty(max(F * 2 * C, 1 << 16), dtype=torch.float32, device=x.device)
+        _gn_ws[key] = ws
+    L.check(lib.pgt_groupnorm_apply_stats(_p(x), _rows(x)[2], F, HW, C, _p(gamma), _p(beta), eps, int(silu), _p(out),
+                                          _rows(out)[2], _p(stats), chunks_per_frame, _p(ws), _stream()))
     return out
 
 

@@ -428,3 +428,35 @@ def test_conv_relu_after_residual():
     o.conv(x.to(DEV), pack_conv_weight(w).to(DEV), C, out, bias=b.to(DEV), act=o.ACT_RELU, residual=res.to(DEV),
            relu_after_res=True)
     check_close(out, F.relu(conv_ref(x, w, b) + res.float()), 'conv relu-after-residual', bf16_out=True)
+
+
+@pytest.mark.parametrize('Fr,H,W,Cin,Cout,lin', [(3, 16, 16, 64, 64, False), (3, 32, 32, 128, 256, False),
+                                                (6, 16, 16, 256, 512, False), (3, 16, 32, 64, 128, False),
+                                                (3, 16, 16, 256, 256, True)])
+def test_groupnorm_stats_fused_in_epilogue(Fr, H, W, Cin, Cout, lin):
+    """conv / linear epilogue emits per-tile (sum, sumsq) per GroupNorm group; finalize+apply consumes them."""
+    o = ops()
+    x = bf(rnd((Fr, H, W, Cin), 150))
+    gam, bet = 1 + 0.1 * rnd((Cout,), 153), 0.1 * rnd((Cout,), 154)
+    res = bf(rnd((Fr, H, W, Cout), 155))
+    y = torch.empty(Fr, H, W, Cout, dtype=torch.bfloat16, device=DEV)
+    if lin:
+        w = bf(rnd((Cout, Cin), 151, Cin ** -0.5))
+        b = rnd((Cout,), 152, 0.1)
+        tpf = H * W // 128
+        stats = torch.zeros(Fr * tpf * 4 * 64, dtype=torch.float32, device=DEV)
+        o.linear(x.to(DEV), w.to(DEV), y, bias=b.to(DEV), residual=res.to(DEV), gn_stats=stats)
+        ref = x.float() @ w.float().t() + b + res.float()
+    else:
+        w = bf(rnd((Cout, Cin, 3, 3), 151, (9 * Cin) ** -0.5)).float()
+        b = rnd((Cout,), 152, 0.1)
+        tpf = o.conv_tiles_per_frame(H, W, Cout)
+        assert tpf > 0
+        stats = torch.zeros(Fr * tpf * 4 * 64, dtype=torch.float32, device=DEV)
+        o.conv(x.to(DEV), pack_conv_weight(w).to(DEV), Cout, y, bias=b.to(DEV), residual=res.to(DEV), gn_stats=stats)
+        ref = conv_ref(x, w, b) + res.float()
+    check_close(y, ref, 'producer', bf16_out=True)
+    out = torch.empty_like(y)
+    o.groupnorm_apply_stats(y, gam.to(DEV), bet.to(DEV), out, stats, tpf * 4)
+    gref = F.silu(F.group_norm(y.float().cpu().permute(0, 3, 1, 2), 32, gam, bet, eps=1e-6)).permute(0, 2, 3, 1)
+    check_close(out, gref, 'fused-stats groupnorm', bf16_out=True, rel=3e-3)
