@@ -141,6 +141,14 @@ int pgt_groupnorm_silu(const void* x, int ldx, int F, int HW, int C, const float
 int pgt_layernorm(const void* x, int ldx, int x_dtype, int T, int C, const float* gamma, const float* beta,
                   float eps, void* y, int ldy, const void* pos, int ldpos, void* y2, int ldy2, void* stream);
 
+/* ---- fused Swin MLP half-block (C = 256):  out = x + fc2(GELU(fc1(LayerNorm(x)))) in ONE kernel — the hidden tile
+ * stays in shared memory / TMEM, x is read once and out written once.  W1, W2: bf16 [C, C] row-major ([out, in]);
+ * gn_stats: optional GroupNorm partials of `out` as in pgt_epilogue.  Returns PGT_ERR_UNSUPPORTED for C != 256.
+ * Replaces norm2 + Mlp + residual of VSTSREncoderTransformerBlock (modules/rstt_layers.py:116-132,335-336). */
+int pgt_swin_mlp_bf16(const void* x, int ldx, int T, int C, const float* ln_g, const float* ln_b, float eps,
+                      const void* W1, const float* b1, const void* W2, const float* b2, void* out, int ldo,
+                      float* gn_stats, void* stream);
+
 /* ---- shifted-window spatio-temporal attention core (3 x 4 x 4 windows, N = 48 tokens).
  * qkv: bf16 [F*H*W, 3C] = [q | k | v] per token in natural (frame, y, x) order; the cyclic
  * shift, window partition / reverse and the {0,-100} shift mask are index math inside the

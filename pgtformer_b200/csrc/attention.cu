@@ -29,16 +29,21 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // =============================================================================== window attention
+// CTA = one 3x4x4 window (48 tokens).  The tokens' full [q | k | v] rows (3C bf16, contiguous in HBM) are staged
+// into shared memory with coalesced 16-byte cp.async copies; warp h then runs head h entirely out of smem
+// (QK^T and PV on mma.sync m16n8k16, fp32 softmax with the relative-position bias and the {0,-100} shift mask),
+// overwrites its own q columns with the result, and the CTA streams the 48 x C output rows back coalesced.
 constexpr int WIN_N = 48;
 
 template <int D>
 __global__ void __launch_bounds__(256)
 window_attn_kernel(const __nv_bfloat16* __restrict__ qkv, int ldqkv, int H, int W, int C, int heads, int shift,
                    const float* __restrict__ bias_tab, __nv_bfloat16* __restrict__ out, int ldo) {
-  constexpr int LDS = D + 8;                               // padded smem row (bf16 elements)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int tok[WIN_N];
   __shared__ int lab[WIN_N];
+  const int LDR = 3 * C + 8;                               // padded smem row (bf16 elements): stride = 4 words mod 32
+  __nv_bfloat16* rows = reinterpret_cast<__nv_bfloat16*>(smem_raw);
   const int nwx = W >> 2;
   const int wx = blockIdx.x % nwx, wy = blockIdx.x / nwx, clip = blockIdx.y;
   if (threadIdx.x < WIN_N) {
@@ -52,40 +57,41 @@ window_attn_kernel(const __nv_bfloat16* __restrict__ qkv, int ldqkv, int H, int 
     lab[i] = hr * 3 + wr;
   }
   __syncthreads();
+  {
+    const int chunks = (3 * C) >> 3;                       // 16-byte chunks per token row
+    for (int i = threadIdx.x; i < WIN_N * chunks; i += 256) {
+      const int r = i / chunks, c = i - r * chunks;
+      cp_async16(rows + (size_t)r * LDR + c * 8, qkv + (size_t)tok[r] * ldqkv + c * 8, true);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+  }
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  __nv_bfloat16* ks = reinterpret_cast<__nv_bfloat16*>(smem_raw) + (size_t)warp * 2 * WIN_N * LDS;
-  __nv_bfloat16* vs = ks + WIN_N * LDS;
   const float scale = rsqrtf((float)D);
   constexpr float LOG2E = 1.4426950408889634f;
 
   for (int h = warp; h < heads; h += 8) {
-    // stage K_h, V_h (48 x D each) into this warp's private smem slab
-    constexpr int CH = D / 8;                              // 16-byte chunks per row
-    for (int i = lane; i < WIN_N * CH; i += 32) {
-      const int r = i / CH, c = i % CH;
-      const __nv_bfloat16* src = qkv + (size_t)tok[r] * ldqkv + C + h * D + c * 8;
-      *reinterpret_cast<uint4*>(ks + r * LDS + c * 8) = __ldg(reinterpret_cast<const uint4*>(src));
-      *reinterpret_cast<uint4*>(vs + r * LDS + c * 8) = __ldg(reinterpret_cast<const uint4*>(src + C));
-    }
-    __syncwarp();
+    const __nv_bfloat16* qs = rows + h * D;
+    const __nv_bfloat16* ks = rows + C + h * D;
+    const __nv_bfloat16* vs = rows + 2 * C + h * D;
     for (int mt = 0; mt < 3; ++mt) {
+      float o[D / 8][4];
       const int r0 = mt * 16 + g, r1 = r0 + 8;
-      const __nv_bfloat16* q0 = qkv + (size_t)tok[r0] * ldqkv + h * D;
-      const __nv_bfloat16* q1 = qkv + (size_t)tok[r1] * ldqkv + h * D;
       float s[6][4];
 #pragma unroll
       for (int nt = 0; nt < 6; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; }
 #pragma unroll
       for (int kk = 0; kk < D / 16; ++kk) {
         uint32_t a[4];
-        a[0] = __ldg(reinterpret_cast<const uint32_t*>(q0 + kk * 16 + 2 * t));
-        a[1] = __ldg(reinterpret_cast<const uint32_t*>(q1 + kk * 16 + 2 * t));
-        a[2] = __ldg(reinterpret_cast<const uint32_t*>(q0 + kk * 16 + 8 + 2 * t));
-        a[3] = __ldg(reinterpret_cast<const uint32_t*>(q1 + kk * 16 + 8 + 2 * t));
+        a[0] = *reinterpret_cast<const uint32_t*>(qs + (size_t)r0 * LDR + kk * 16 + 2 * t);
+        a[1] = *reinterpret_cast<const uint32_t*>(qs + (size_t)r1 * LDR + kk * 16 + 2 * t);
+        a[2] = *reinterpret_cast<const uint32_t*>(qs + (size_t)r0 * LDR + kk * 16 + 8 + 2 * t);
+        a[3] = *reinterpret_cast<const uint32_t*>(qs + (size_t)r1 * LDR + kk * 16 + 8 + 2 * t);
 #pragma unroll
         for (int nt = 0; nt < 6; ++nt) {
-          const __nv_bfloat16* kr = ks + (nt * 8 + g) * LDS + kk * 16 + 2 * t;
+          const __nv_bfloat16* kr = ks + (size_t)(nt * 8 + g) * LDR + kk * 16 + 2 * t;
           mma_bf16_16816(s[nt], a, *reinterpret_cast<const uint32_t*>(kr), *reinterpret_cast<const uint32_t*>(kr + 8));
         }
       }
@@ -127,7 +133,6 @@ window_attn_kernel(const __nv_bfloat16* __restrict__ qkv, int ldqkv, int H, int 
       sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
       const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
       // O = P V  (P normalised in fp32 before the bf16 pack, as the reference's softmax output is)
-      float o[D / 8][4];
 #pragma unroll
       for (int nt = 0; nt < D / 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
 #pragma unroll
@@ -140,19 +145,28 @@ window_attn_kernel(const __nv_bfloat16* __restrict__ qkv, int ldqkv, int H, int 
 #pragma unroll
         for (int nt = 0; nt < D / 8; ++nt) {
           uint32_t b0, b1;
-          ldmatrix_x2_trans(b0, b1, vs + (kk * 16 + (lane & 15)) * LDS + nt * 8);
+          ldmatrix_x2_trans(b0, b1, vs + (size_t)(kk * 16 + (lane & 15)) * LDR + nt * 8);
           mma_bf16_16816(o[nt], a, b0, b1);
         }
       }
-      __nv_bfloat16* o0 = out + (size_t)tok[r0] * ldo + h * D;
-      __nv_bfloat16* o1 = out + (size_t)tok[r1] * ldo + h * D;
+      // only this row tile reads q rows [mt*16, mt*16+16) of head h: overwrite them with the head's output
+      __syncwarp();
+      __nv_bfloat16* o0 = rows + (size_t)r0 * LDR + h * D;
+      __nv_bfloat16* o1 = rows + (size_t)r1 * LDR + h * D;
 #pragma unroll
       for (int nt = 0; nt < D / 8; ++nt) {
         *reinterpret_cast<uint32_t*>(o0 + nt * 8 + 2 * t) = pack_bf16x2(o[nt][0], o[nt][1]);
         *reinterpret_cast<uint32_t*>(o1 + nt * 8 + 2 * t) = pack_bf16x2(o[nt][2], o[nt][3]);
       }
     }
-    __syncwarp();
+  }
+  __syncthreads();
+  {
+    const int chunks = C >> 3;                             // 16-byte chunks per output row
+    for (int i = threadIdx.x; i < WIN_N * chunks; i += 256) {
+      const int r = i / chunks, c = i - r * chunks;
+      *reinterpret_cast<uint4*>(out + (size_t)tok[r] * ldo + c * 8) = *reinterpret_cast<const uint4*>(rows + (size_t)r * LDR + c * 8);
+    }
   }
 }
 
@@ -299,7 +313,7 @@ extern "C" int pgt_window_attention(const void* qkv, int ldqkv, int clips, int H
   const int d = C / heads;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid((H / 4) * (W / 4), clips);
-  const size_t smem = (size_t)8 * 2 * WIN_N * (d + 8) * 2;
+  const size_t smem = (size_t)WIN_N * (3 * C + 8) * 2;
   ProfScope ps(PGT_PROF_WINDOW_ATTN, 4.0 * WIN_N * WIN_N * C * (double)grid.x * grid.y, st);
   if (d == 32) {
     static bool attr32 = false;

@@ -114,6 +114,7 @@ class Engine:
     def _new(self, *shape, dtype=BF):
         return torch.empty(*shape, dtype=dtype, device=self.dev)
 
+    fuse_swin_mlp = True      # LN + fc1 + GELU + fc2 + residual of the C=256 Swin blocks as one kernel
     fuse_gn_stats = True      # GroupNorm statistics from the producing conv / linear epilogue (saves one pass)
 
     def _gn(self, x, p, silu=True):
@@ -164,6 +165,17 @@ class Engine:
         qkv = self._lin(y, p + '.attn.qkv', 3 * C)
         a = ops.window_attention(qkv, Fr // 3, H, W, C, heads, shift, w[p + '.attn.bias_tab'], self._new(Fr, H, W, C))
         x = self._lin(a, p + '.attn.proj', C, residual=x)
+        if C == 256 and self.fuse_swin_mlp:
+            # norm2 + fc1 + GELU + fc2 + residual in one kernel (the hidden tile never leaves the SM)
+            out = self._new(Fr, H, W, C)
+            stats = None
+            if gn_next and self.fuse_gn_stats and (H * W) % 128 == 0:
+                tpf = H * W // 128
+                stats = self._new(Fr * tpf * 4 * 64, dtype=torch.float32)
+                out._pgt_gn = (stats, tpf * 4)
+            return ops.swin_mlp(x, w[p + '.norm2.weight'], w[p + '.norm2.bias'], w[p + '.mlp.fc1.weight'],
+                                w[p + '.mlp.fc1.bias'], w[p + '.mlp.fc2.weight'], w[p + '.mlp.fc2.bias'], out,
+                                gn_stats=stats)
         y = ops.layernorm(x, w[p + '.norm2.weight'], w[p + '.norm2.bias'], self._new(Fr, H, W, C))
         m = self._lin(y, p + '.mlp.fc1', C, act=ops.ACT_GELU)
         return self._lin(m, p + '.mlp.fc2', C, residual=x, gn_out=gn_next)

@@ -170,6 +170,16 @@ def layernorm(x, gamma, beta, out, eps=1e-5, pos=None, out2=None):
     return out
 
 
+def swin_mlp(x, ln_g, ln_b, w1, b1, w2, b2, out, eps=1e-5, gn_stats=None):
+    """out = x + fc2(gelu(fc1(LN(x)))) fused (C == 256); x, out: [..., C] bf16 with a uniform row stride."""
+    lib = L.load()
+    T, C, ldx = _rows(x)
+    assert x.dtype == torch.bfloat16 and w1.dtype == torch.bfloat16 and w1.is_contiguous() and w2.is_contiguous()
+    L.check(lib.pgt_swin_mlp_bf16(_p(x), ldx, T, C, _p(ln_g), _p(ln_b), eps, _p(w1), _p(b1), _p(w2), _p(b2), _p(out),
+                                  _rows(out)[2], _p(gn_stats), _stream()))
+    return out
+
+
 def window_attention(qkv, clips, H, W, C, heads, shift, bias_tab, out):
     lib = L.load()
     assert qkv.dtype == torch.bfloat16 and bias_tab.dtype == torch.float32 and bias_tab.is_contiguous()

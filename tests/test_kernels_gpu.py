@@ -460,3 +460,21 @@ def test_groupnorm_stats_fused_in_epilogue(Fr, H, W, Cin, Cout, lin):
     o.groupnorm_apply_stats(y, gam.to(DEV), bet.to(DEV), out, stats, tpf * 4)
     gref = F.silu(F.group_norm(y.float().cpu().permute(0, 3, 1, 2), 32, gam, bet, eps=1e-6)).permute(0, 2, 3, 1)
     check_close(out, gref, 'fused-stats groupnorm', bf16_out=True, rel=3e-3)
+
+
+@pytest.mark.parametrize('T', [128, 1000, 12288])
+def test_swin_mlp_fused(T):
+    """out = x + fc2(gelu(fc1(LN(x)))) in one kernel vs the fp32 composition on bf16-rounded operands."""
+    o = ops()
+    C = 256
+    x = bf(rnd((T, C), 160) * 1.5 + 0.1)
+    g, b = 1 + 0.1 * rnd((C,), 161), 0.1 * rnd((C,), 162)
+    w1, b1 = bf(rnd((C, C), 163, C ** -0.5)), rnd((C,), 164, 0.1)
+    w2, b2 = bf(rnd((C, C), 165, C ** -0.5)), rnd((C,), 166, 0.1)
+    out = torch.empty(T, C, dtype=torch.bfloat16, device=DEV)
+    o.swin_mlp(x.to(DEV), g.to(DEV), b.to(DEV), w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV), out)
+    torch.cuda.synchronize()
+    y = bf(F.layer_norm(x.float(), (C,), g, b, 1e-5)).float()
+    hdn = bf(F.gelu(y @ w1.float().t() + b1)).float()
+    ref = x.float() + hdn @ w2.float().t() + b2
+    check_close(out, ref, 'fused swin mlp', bf16_out=True, rel=4e-3)
