@@ -108,9 +108,21 @@ int pgt_conv_bf16(const void* x, int F, int Hin, int Win, int Cin, int ldx, cons
  * A traffic.  Wp4: bf16 [4 phases][Cout][4*CinPad], phase = py*2+px, K index = (ty*2+tx)*CinPad + c, where
  * taps of phase p are the sums w[Sy(ty), Sx(tx)] with S(0) = {0} / {0,1} and S(1) = {1,2} / {2} for p = 0 / 1
  * (packed by pgtformer_b200/engine.py::_pack_up2x).  ep->out is the [F, 2Hin, 2Win, Cout] result.
+ * ep->gn_stats (optional): fp32 [F][4 phases][tiles per phase-frame][4][32][2], i.e. 16 * tiles chunks per frame
+ * with tiles = pgt_conv_tiles_per_frame(Hin, Win, Cout, 2, 1, 1).
  * Replaces Upsample.forward (archs/tdcrqvae3_arch.py:45-52). */
 int pgt_conv_up2x_bf16(const void* x, int F, int Hin, int Win, int Cin, int ldx, const void* Wp4, int ldw,
                        int Cout, const pgt_epilogue* ep, void* stream);
+
+/* ---- im2col of an fp32 NCHW RGB image for the two Cin = 3 convolutions (encoder conv_in 3x3/1 and the BiSeNet stem
+ * 7x7/2): out[(f, oy, ox), (ky*ksize + kx)*3 + c] = (x[f, c, oy*stride - pad + ky, ox*stride - pad + kx] - mean[c]) /
+ * std[c], zero outside the image and in the K padding columns; out: bf16 [F*Ho*Wo, ldo], ldo % 8 == 0,
+ * ldo >= 3*ksize^2.  mean / std: HOST pointers to 3 floats or NULL.  The GEMM that follows (pgt_linear_bf16) then
+ * runs these convs on the tensor cores with the usual fused epilogue.
+ * Replaces the input side of Encoder.conv_in (archs/tdcrqvae3_arch.py:500-504) and Resnet18.conv1
+ * (archs/pgtformer_arch.py:95-99). */
+int pgt_im2col_rgb(const float* x_nchw, int F, int H, int W, int ksize, int stride, int pad, const float* mean3,
+                   const float* std3, void* out, int ldo, void* stream);
 
 /* ---- first conv of the encoder: 3x3, Cin=3, fp32 NCHW input -> NHWC bf16 (direct FFMA kernel;
  * K = 27 is too small for the tensor pipe).  w: fp32 [Cout,3,3,3] (OIHW), bias fp32 [Cout].

@@ -48,27 +48,40 @@ struct ProfScope {      // RAII: events around one launch when the profiler is o
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ---- device math
-// exact-erf GELU with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): 1 rcp + 1 ex2 + 6 fma instead of
-// the multi-branch libdevice erff, which dominated the GEMM epilogue
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// exact-erf GELU, v * Phi(v), with erfc from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7):
+//   w = erfc(|v| / sqrt 2) = t * poly(t) * exp(-v^2 / 2),  t = 1 / (1 + p |v| / sqrt 2)
+//   gelu(v) = relu(v) - 0.5 |v| w          (v >= 0: v (1 - w/2);  v < 0: v w / 2)
+// 2 MUFU + 12 FP32 ops, no branches — the multi-branch libdevice erff dominated the GEMM epilogue
 __device__ __forceinline__ float gelu_erf(float v) {
-  const float z = fabsf(v) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float az = fabsf(v);
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, az, 1.0f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = 1.0f - poly * t * __expf(-z * z);
-  const float erf_v = copysignf(erf_abs, v);
-  return 0.5f * v * (1.0f + erf_v);
+  const float e = ex2_approx(v * v * (-0.5f * 1.4426950408889634f));
+  const float w = poly * t * e;
+  return fmaf(az * -0.5f, w, fmaxf(v, 0.f));
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
     case PGT_ACT_GELU: return gelu_erf(v);
-    case PGT_ACT_SILU: return v / (1.0f + __expf(-v));
+    case PGT_ACT_SILU: return v * rcp_approx(1.0f + ex2_approx(v * -1.4426950408889634f));
     case PGT_ACT_LRELU02: return v > 0.f ? v : 0.2f * v;
     case PGT_ACT_RELU: return fmaxf(v, 0.f);
-    case PGT_ACT_SIGMOID: return 1.0f / (1.0f + __expf(-v));
+    case PGT_ACT_SIGMOID: return rcp_approx(1.0f + ex2_approx(v * -1.4426950408889634f));
     default: return v;
   }
 }

@@ -57,6 +57,8 @@ struct GemmParams {
   int act, epi_mode;
   float* gn_stats;       // optional: per-(tile, group) partial (sum, sumsq) of the OUTPUT for the next GroupNorm(32)
   int gn_cpg;            // channels per group = N / 32
+  int gn_tpf;            // > 0: statistics rows are laid out [frame][gn_fstride] (several launches share one buffer)
+  int gn_fstride;        //      chunk = (m_blk / gn_tpf) * gn_fstride + (m_blk % gn_tpf) * 4 + quad
   int relu_after_res;    // ResNet BasicBlock: out = relu(conv + shortcut) — ReLU applied after the residual add
   const void* residual;
   int ldr, res_dtype;
@@ -342,7 +344,11 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, const EpiCtx&
           const int col0 = col_base + pcol + sub * 32;
           const float* b32 = bias_vec ? p.bias + col0 : nullptr;
           float* gq = nullptr;
-          if (p.gn_stats != nullptr) gq = p.gn_stats + (((size_t)m_blk * 4 + quad) * 32 + col0 / p.gn_cpg) * 2;
+          if (p.gn_stats != nullptr) {
+            const size_t chunk = p.gn_tpf > 0 ? (size_t)(m_blk / p.gn_tpf) * p.gn_fstride + (m_blk % p.gn_tpf) * 4 + quad
+                                              : (size_t)m_blk * 4 + quad;
+            gq = p.gn_stats + (chunk * 32 + col0 / p.gn_cpg) * 2;
+          }
           if (sft) epi_chunk<true>(p, t_row + pcol + sub * 32, b32, srow, r, sub, esize, true, gq, col0);
           else epi_chunk<false>(p, t_row + pcol + sub * 32, b32, srow, r, sub, esize, p.has_res_map != 0, gq, col0);
         }
@@ -831,7 +837,7 @@ static int setup_epilogue_maps(GemmParams& p, const CUtensorMap& placeholder, CU
   if (p.gn_stats != nullptr) {
     // fused GroupNorm statistics live on the bf16 TMA-store path; every 128-row tile must sit inside one frame
     const int cpg = p.N / 32;
-    const bool ok = p.fast_epi && p.out_dtype == PGT_BF16 && (p.N % 32) == 0 && p.o_sx == 0 &&
+    const bool ok = p.fast_epi && p.out_dtype == PGT_BF16 && (p.N % 32) == 0 &&
                     (cpg == 2 || cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32) &&
                     (p.mode == MODE_LINEAR || p.tn == 1);
     if (!ok) return PGT_ERR_UNSUPPORTED;
@@ -1048,6 +1054,14 @@ static int conv_impl(const void* x, int F, int Hin, int Win, int Cin, int ldx, c
   p.m_tiles = p.tiles_x * p.tiles_y * ceil_div(F, tn);
   p.M = F * p.H * p.W;
   p.flops = 2.0 * p.M * (double)Cout * (ksize * ksize * Cin);
+  if (up_phase >= 0 && p.gn_stats != nullptr) {
+    // the four phase launches share one statistics buffer [frame][phase][tile][quadrant][32][2]
+    if (tn != 1) return PGT_ERR_UNSUPPORTED;
+    const int tpf = p.tiles_x * p.tiles_y;
+    p.gn_tpf = tpf;
+    p.gn_fstride = 16 * tpf;
+    p.gn_stats += (size_t)up_phase * tpf * 4 * 64;
+  }
   if (p.mode == MODE_CONV_S1) {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)F};
     uint64_t str[3] = {(uint64_t)ldx * 2, (uint64_t)Win * ldx * 2, (uint64_t)Hin * Win * ldx * 2};

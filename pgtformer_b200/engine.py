@@ -58,6 +58,11 @@ def _pack_lin(w):
     return w.to(BF).contiguous()
 
 
+def _pack_rgb(w):
+    """[Cout, 3, k, k] fp32 -> [Cout, roundup(3*k*k, 8)] bf16 with K index (ky*k + kx)*3 + c (ops.im2col_rgb order)."""
+    return _pack_lin(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1))
+
+
 class Engine:
     def __init__(self, network_g, state_dict, device):
         ops.L.load()                                   # fail loudly if the CUDA library is missing
@@ -80,7 +85,7 @@ class Engine:
                 continue
             if name.endswith('.weight') and t.dim() == 4:
                 if name == 'encoder.conv_in.weight':
-                    w[name] = t.float().contiguous()
+                    w[name] = _pack_rgb(t.float())
                 elif t.shape[2] == 3 and '.upsample.conv.' in name:
                     w[name] = _pack_up2x(t.float())
                 elif t.shape[2] == 3:
@@ -227,11 +232,11 @@ class Engine:
         def put(key, conv, bn, kind):
             wt, bias = fold(conv, bn)
             w['bn.' + key + '.weight'] = {'c3': _pack_conv, 'up': _pack_up2x, 'lin': _pack_lin,
-                                          'raw': lambda t: t.contiguous()}[kind](wt)
+                                          'rgb': _pack_rgb}[kind](wt)
             if bias is not None:
                 w['bn.' + key + '.bias'] = bias
 
-        put('stem', 'cp.resnet.conv1', 'cp.resnet.bn1', 'raw')
+        put('stem', 'cp.resnet.conv1', 'cp.resnet.bn1', 'rgb')
         for li in (1, 2, 3, 4):
             for bi in (0, 1):
                 p = 'cp.resnet.layer%d.%d' % (li, bi)
@@ -280,8 +285,11 @@ class Engine:
         into the stem) -> conditioning map [F, H/16, W/16, 64] bf16 (57 channels used, zero padded)."""
         Fr, _, H, W = x.shape
         w = self.w
-        t = ops.stem7x7(x, (0.485, 0.456, 0.406), (0.229, 0.224, 0.225), w['bn.stem.weight'], w['bn.stem.bias'],
-                        self._new(Fr, H // 2, W // 2, 64))
+        # 7x7/2 stem as im2col (ImageNet normalisation applied on the fly) + tensor-core GEMM with the folded BN + ReLU
+        cols = ops.im2col_rgb(x, 7, 2, 3, self._new(Fr * (H // 2) * (W // 2), w['bn.stem.weight'].shape[1]),
+                              (0.485, 0.456, 0.406), (0.229, 0.224, 0.225))
+        t = ops.linear(cols, w['bn.stem.weight'], self._new(Fr, H // 2, W // 2, 64), bias=w['bn.stem.bias'], N=64,
+                       act=ops.ACT_RELU)
         t = ops.maxpool3x3s2(t, self._new(Fr, H // 4, W // 4, 64))
         feats = []
         for li, cout, stride in ((1, 64, 1), (2, 128, 2), (3, 256, 2), (4, 512, 2)):
@@ -323,7 +331,10 @@ class Engine:
         """Encoder.forward (`archs/tdcrqvae3_arch.py:540-573`); x fp32 NCHW -> (h [F,h,w,z], feats)."""
         a = self.arch
         Fr, _, H, W = x.shape
-        h = ops.conv_in_rgb(x, self.w['encoder.conv_in.weight'], self.w['encoder.conv_in.bias'], self._new(Fr, H, W, a.ch))
+        # Cin = 3: im2col to a [pixels, 32] patch matrix, then the ordinary GEMM (its epilogue also yields the
+        # GroupNorm statistics block 0's norm1 needs)
+        cols = ops.im2col_rgb(x, 3, 1, 1, self._new(Fr * H * W, self.w['encoder.conv_in.weight'].shape[1]))
+        h = self._lin(cols, 'encoder.conv_in', a.ch, out=self._new(Fr, H, W, a.ch), gn_out=True)
         feats = []
         for lvl in range(a.num_levels):
             last = lvl == a.num_levels - 1
@@ -370,7 +381,13 @@ class Engine:
             if lvl != 0:
                 Fr, H, W, C = h.shape
                 p = 'decoder.up.%d.upsample.conv' % lvl
-                h = ops.conv_up2x(h, self.w[p + '.weight'], C, self._new(Fr, 2 * H, 2 * W, C), bias=self.w[p + '.bias'])
+                out = self._new(Fr, 2 * H, 2 * W, C)
+                stats = None
+                tpf = ops.conv_tiles_per_frame(H, W, C, 2, 1, 1)
+                if self.fuse_gn_stats and tpf > 0 and C // 32 in (2, 4, 8, 16, 32):
+                    stats = self._new(Fr * 16 * tpf * 64, dtype=torch.float32)     # [frame][phase][tile][quadrant][32][2]
+                    out._pgt_gn = (stats, 16 * tpf)
+                h = ops.conv_up2x(h, self.w[p + '.weight'], C, out, bias=self.w[p + '.bias'], gn_stats=stats)
         Fr, H, W, _ = h.shape
         out = self._new(Fr, a.out_ch, H, W, dtype=torch.float32)
         self._conv3(self._gn(h, 'decoder.norm_out'), 'decoder.conv_out', a.out_ch, out=out, nchw=True)

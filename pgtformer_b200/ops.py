@@ -99,13 +99,24 @@ def conv(x, wp, cout, out, ksize=3, stride=1, pad_lo=1, bias=None, act=ACT_NONE,
     return out
 
 
-def conv_up2x(x, wp4, cout, out, bias=None, act=ACT_NONE):
+def im2col_rgb(x_nchw, ksize, stride, pad, out, mean3=None, std3=None):
+    """fp32 NCHW RGB -> bf16 [F*Ho*Wo, Kpad] patch matrix, K index (ky*ksize+kx)*3 + c; optional (x-mean)/std."""
+    lib = L.load()
+    F, C, H, W = x_nchw.shape
+    assert C == 3 and x_nchw.dtype == torch.float32 and x_nchw.is_contiguous() and out.is_contiguous()
+    m = (ctypes.c_float * 3)(*[float(v) for v in mean3]) if mean3 is not None else None
+    s = (ctypes.c_float * 3)(*[float(v) for v in std3]) if std3 is not None else None
+    L.check(lib.pgt_im2col_rgb(_p(x_nchw), F, H, W, ksize, stride, pad, m, s, _p(out), out.shape[-1], _stream()))
+    return out
+
+
+def conv_up2x(x, wp4, cout, out, bias=None, act=ACT_NONE, gn_stats=None):
     """nearest x2 upsample + conv3x3 folded into four 2x2 phase convs; wp4 [4, cout, 4*CinPad] bf16."""
     lib = L.load()
     F, H, W, Cin = x.shape
     assert x.dtype == torch.bfloat16 and wp4.dtype == torch.bfloat16 and wp4.is_contiguous() and wp4.dim() == 3
     assert tuple(out.shape) == (F, 2 * H, 2 * W, cout) and out.is_contiguous()
-    ep = make_epilogue(out, bias, act)
+    ep = make_epilogue(out, bias, act, gn_stats=gn_stats)
     L.check(lib.pgt_conv_up2x_bf16(_p(x), F, H, W, Cin, x.stride(2), _p(wp4), wp4.stride(1), cout, ctypes.byref(ep),
                                    _stream()))
     return out

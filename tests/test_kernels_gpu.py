@@ -478,3 +478,50 @@ def test_swin_mlp_fused(T):
     hdn = bf(F.gelu(y @ w1.float().t() + b1)).float()
     ref = x.float() + hdn @ w2.float().t() + b2
     check_close(out, ref, 'fused swin mlp', bf16_out=True, rel=4e-3)
+
+
+@pytest.mark.parametrize('Fr,H,W,C', [(3, 16, 16, 128), (2, 32, 64, 64), (3, 16, 16, 512)])
+def test_conv_up2x_groupnorm_stats(Fr, H, W, C):
+    """The four phase launches of the upsample conv fill one statistics buffer [frame][phase][tile][quad][32][2]."""
+    from pgtformer_b200.engine import _pack_up2x
+    o = ops()
+    x = bf(rnd((Fr, H, W, C), 170))
+    w = bf(rnd((C, C, 3, 3), 171, (9 * C) ** -0.5)).float()
+    b = rnd((C,), 172, 0.1)
+    gam, bet = 1 + 0.1 * rnd((C,), 173), 0.1 * rnd((C,), 174)
+    tpf = o.conv_tiles_per_frame(H, W, C, 2, 1, 1)
+    assert tpf > 0
+    stats = torch.zeros(Fr * 16 * tpf * 64, dtype=torch.float32, device=DEV)
+    y = torch.empty(Fr, 2 * H, 2 * W, C, dtype=torch.bfloat16, device=DEV)
+    o.conv_up2x(x.to(DEV), _pack_up2x(w.to(DEV)), C, y, bias=b.to(DEV), gn_stats=stats)
+    out = torch.empty_like(y)
+    o.groupnorm_apply_stats(y, gam.to(DEV), bet.to(DEV), out, stats, 16 * tpf)
+    gref = F.silu(F.group_norm(y.float().cpu().permute(0, 3, 1, 2), 32, gam, bet, eps=1e-6)).permute(0, 2, 3, 1)
+    check_close(out, gref, 'up2x fused-stats groupnorm', bf16_out=True, rel=3e-3)
+
+
+@pytest.mark.parametrize('ks,stride,pad,norm', [(3, 1, 1, False), (7, 2, 3, True)])
+def test_im2col_rgb_then_gemm(ks, stride, pad, norm):
+    """Cin = 3 convs (encoder conv_in, BiSeNet stem) as im2col + tensor-core GEMM: the patch matrix is bit-exact
+    against unfold on bf16-rounded inputs, the GEMM result matches conv2d."""
+    from pgtformer_b200.engine import _pack_rgb
+    o = ops()
+    Fr, H, W = 3, 32, 48
+    x = torch.rand(Fr, 3, H, W, generator=torch.Generator().manual_seed(180))
+    mean, std = ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225)) if norm else (None, None)
+    w, b = rnd((64, 3, ks, ks), 181, (3 * ks * ks) ** -0.5), rnd((64,), 182, 0.1)
+    wp = _pack_rgb(w.to(DEV))
+    Ho, Wo = (H + 2 * pad - ks) // stride + 1, (W + 2 * pad - ks) // stride + 1
+    cols = torch.full((Fr * Ho * Wo, wp.shape[1]), 7.0, dtype=torch.bfloat16, device=DEV)
+    o.im2col_rgb(x.to(DEV), ks, stride, pad, cols, mean, std)
+    xn = x if not norm else (x - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+    u = F.unfold(xn, ks, padding=pad, stride=stride)                       # [F, 3*ks*ks (c-major), L]
+    u = u.view(Fr, 3, ks * ks, Ho * Wo).permute(0, 3, 2, 1).reshape(Fr * Ho * Wo, ks * ks * 3)
+    got = cols.float().cpu()
+    assert torch.all(got[:, 3 * ks * ks:] == 0)
+    # (x - mean) * (1 / std) vs (x - mean) / std differ by an fp32 ulp before the bf16 rounding
+    assert (got[:, :3 * ks * ks] - bf(u).float()).abs().max().item() <= (2 ** -6 if norm else 0.0)
+    out = torch.empty(Fr, Ho, Wo, 64, dtype=torch.bfloat16, device=DEV)
+    o.linear(cols, wp, out, bias=b.to(DEV), N=64, act=o.ACT_RELU)
+    ref = F.relu(F.conv2d(bf(xn).float(), bf(w).float(), b, stride=stride, padding=pad)).permute(0, 2, 3, 1)
+    check_close(out, ref, 'rgb conv via im2col', bf16_out=True)

@@ -42,5 +42,14 @@ elif which == 'linear256':
     out = torch.empty(M, 256, device=dev, dtype=torch.bfloat16)
     for _ in range(3):
         ops.linear(a, w, out, bias=b, residual=res)
+elif which == 'swin_mlp':
+    M = 786432 // 4
+    x = torch.randn(M, 256, device=dev).bfloat16()
+    w1 = (torch.randn(256, 256, device=dev) * 0.05).bfloat16()
+    w2 = (torch.randn(256, 256, device=dev) * 0.05).bfloat16()
+    g, b = torch.ones(256, device=dev), torch.zeros(256, device=dev)
+    out = torch.empty_like(x)
+    for _ in range(3):
+        ops.swin_mlp(x, g, b, w1, b, w2, b, out)
 torch.cuda.synchronize()
 print('done', which)
