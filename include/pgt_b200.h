@@ -114,15 +114,17 @@ int pgt_conv_bf16(const void* x, int F, int Hin, int Win, int Cin, int ldx, cons
 int pgt_conv_up2x_bf16(const void* x, int F, int Hin, int Win, int Cin, int ldx, const void* Wp4, int ldw,
                        int Cout, const pgt_epilogue* ep, void* stream);
 
-/* ---- im2col of an fp32 NCHW RGB image for the two Cin = 3 convolutions (encoder conv_in 3x3/1 and the BiSeNet stem
- * 7x7/2): out[(f, oy, ox), (ky*ksize + kx)*3 + c] = (x[f, c, oy*stride - pad + ky, ox*stride - pad + kx] - mean[c]) /
- * std[c], zero outside the image and in the K padding columns; out: bf16 [F*Ho*Wo, ldo], ldo % 8 == 0,
- * ldo >= 3*ksize^2.  mean / std: HOST pointers to 3 floats or NULL.  The GEMM that follows (pgt_linear_bf16) then
- * runs these convs on the tensor cores with the usual fused epilogue.
- * Replaces the input side of Encoder.conv_in (archs/tdcrqvae3_arch.py:500-504) and Resnet18.conv1
- * (archs/pgtformer_arch.py:95-99). */
-int pgt_im2col_rgb(const float* x_nchw, int F, int H, int W, int ksize, int stride, int pad, const float* mean3,
-                   const float* std3, void* out, int ldo, void* stream);
+/* ---- the two Cin = 3 convolutions on the tensor cores, reading the fp32 NCHW image directly (im2col inside the
+ * kernel): ksize/stride/pad = 3/1/1 (Encoder.conv_in, archs/tdcrqvae3_arch.py:500-504) or 7/2/3 (Resnet18.conv1 +
+ * folded bn1 + relu, archs/pgtformer_arch.py:95-99,110-112); Cout = 64.
+ *   Wp: bf16 [Cout, ldw], K index (ky*ksize + kx)*3 + c, ldw % 8 == 0;  mean3 / std3: HOST pointers to 3 floats or
+ *   NULL: the input is (x - mean) / std with zero padding applied after the normalisation, as in the reference;
+ *   act: PGT_ACT_NONE or PGT_ACT_RELU;  out: bf16 [F*Ho*Wo, ldo];  gn_stats: optional GroupNorm partials of the
+ *   output, fp32 [ceil(F*Ho*Wo/128)][4][32][2] (requires Ho*Wo % 128 == 0).
+ * PGT_ERR_UNSUPPORTED for any other geometry. */
+int pgt_conv_rgb_bf16(const float* x_nchw, int F, int H, int W, int ksize, int stride, int pad, const float* mean3,
+                      const float* std3, const void* Wp, int ldw, int Cout, const float* bias, int act, void* out,
+                      int ldo, float* gn_stats, void* stream);
 
 /* ---- first conv of the encoder: 3x3, Cin=3, fp32 NCHW input -> NHWC bf16 (direct FFMA kernel;
  * K = 27 is too small for the tensor pipe).  w: fp32 [Cout,3,3,3] (OIHW), bias fp32 [Cout].

@@ -38,8 +38,8 @@ SIGNATURES = {
                               c_int, POINTER(Epilogue), c_void_p]),
     'pgt_conv_up2x_bf16': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                    POINTER(Epilogue), c_void_p]),
-    'pgt_im2col_rgb': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
-                               c_void_p]),
+    'pgt_conv_rgb_bf16': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                  c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     'pgt_conv_in_rgb': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     'pgt_groupnorm_ws_floats': (c_int64, [c_int, c_int, c_int]),
     'pgt_conv_tiles_per_frame': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),

@@ -238,65 +238,6 @@ extern "C" int pgt_conv_in_rgb(const float* x_nchw, int F, int H, int W, const f
   return PGT_OK;
 }
 
-// ---- im2col for the Cin = 3 convolutions: thread = one 16-byte chunk (8 consecutive K entries) of one output row
-namespace pgt {
-struct Im2colParams {
-  int H, W, Ho, Wo, ks, stride, pad, K, nch;
-  float mean[3], istd[3];
-};
-__global__ void __launch_bounds__(256) im2col_rgb_kernel(const float* __restrict__ x, size_t total, const Im2colParams p,
-                                                          __nv_bfloat16* __restrict__ out, int ldo) {
-  const size_t plane = (size_t)p.H * p.W;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % p.nch);
-    const size_t row = i / p.nch;
-    const int ox = (int)(row % p.Wo);
-    const size_t r2 = row / p.Wo;
-    const int oy = (int)(r2 % p.Ho);
-    const size_t f = r2 / p.Ho;
-    const float* xf = x + f * 3 * plane;
-    const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = ch * 8 + j;
-      const int tap = k / 3, c = k - tap * 3;
-      const int ky = tap / p.ks, kx = tap - ky * p.ks;
-      const int iy = iy0 + ky, ix = ix0 + kx;
-      const bool ok = k < p.K && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-      v[j] = ok ? (__ldg(xf + c * plane + (size_t)iy * p.W + ix) - p.mean[c]) * p.istd[c] : 0.f;
-    }
-    uint4 u;
-    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(out + row * ldo + ch * 8) = u;
-  }
-}
-}  // namespace pgt
-
-extern "C" int pgt_im2col_rgb(const float* x_nchw, int F, int H, int W, int ksize, int stride, int pad, const float* mean3,
-                              const float* std3, void* out, int ldo, void* stream) {
-  PGT_CHECK_ARG(x_nchw && out && F > 0 && H > 0 && W > 0 && ksize >= 1 && ksize <= 7 && stride >= 1 && pad >= 0);
-  PGT_CHECK_ARG(ldo % 8 == 0 && ldo >= 3 * ksize * ksize && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  pgt::Im2colParams p;
-  p.H = H; p.W = W; p.ks = ksize; p.stride = stride; p.pad = pad;
-  p.Ho = (H + 2 * pad - ksize) / stride + 1;
-  p.Wo = (W + 2 * pad - ksize) / stride + 1;
-  PGT_CHECK_ARG(p.Ho > 0 && p.Wo > 0);
-  p.K = 3 * ksize * ksize;
-  p.nch = ldo / 8;
-  for (int c = 0; c < 3; ++c) {
-    p.mean[c] = mean3 ? mean3[c] : 0.f;
-    p.istd[c] = std3 ? 1.f / std3[c] : 1.f;
-  }
-  const size_t total = (size_t)F * p.Ho * p.Wo * p.nch;
-  ProfScope ps(PGT_PROF_MOVE, (double)F * H * W * 12.0 + (double)total * 16.0, static_cast<cudaStream_t>(stream), "pgt_im2col_rgb");
-  const unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)148 * 64);
-  pgt::im2col_rgb_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x_nchw, total, p,
-                                                                            reinterpret_cast<__nv_bfloat16*>(out), ldo);
-  PGT_LAUNCH_OK();
-  return PGT_OK;
-}
-
 // ---- temporal regroup used by the SFT fusion block's cross-frame 1x1 mixers
 // dir 0: x [b,3,P,C] -> y [b,P,3*C] (channel = frame*C + c);   dir 1: the inverse.
 namespace pgt {

@@ -285,11 +285,9 @@ class Engine:
         into the stem) -> conditioning map [F, H/16, W/16, 64] bf16 (57 channels used, zero padded)."""
         Fr, _, H, W = x.shape
         w = self.w
-        # 7x7/2 stem as im2col (ImageNet normalisation applied on the fly) + tensor-core GEMM with the folded BN + ReLU
-        cols = ops.im2col_rgb(x, 7, 2, 3, self._new(Fr * (H // 2) * (W // 2), w['bn.stem.weight'].shape[1]),
-                              (0.485, 0.456, 0.406), (0.229, 0.224, 0.225))
-        t = ops.linear(cols, w['bn.stem.weight'], self._new(Fr, H // 2, W // 2, 64), bias=w['bn.stem.bias'], N=64,
-                       act=ops.ACT_RELU)
+        # 7x7/2 stem on the tensor cores (im2col + ImageNet normalisation inside the kernel, folded BN + ReLU epilogue)
+        t = ops.conv_rgb(x, w['bn.stem.weight'], w['bn.stem.bias'], self._new(Fr, H // 2, W // 2, 64), 7, 2, 3,
+                         act=ops.ACT_RELU, mean3=(0.485, 0.456, 0.406), std3=(0.229, 0.224, 0.225))
         t = ops.maxpool3x3s2(t, self._new(Fr, H // 4, W // 4, 64))
         feats = []
         for li, cout, stride in ((1, 64, 1), (2, 128, 2), (3, 256, 2), (4, 512, 2)):
@@ -331,10 +329,14 @@ class Engine:
         """Encoder.forward (`archs/tdcrqvae3_arch.py:540-573`); x fp32 NCHW -> (h [F,h,w,z], feats)."""
         a = self.arch
         Fr, _, H, W = x.shape
-        # Cin = 3: im2col to a [pixels, 32] patch matrix, then the ordinary GEMM (its epilogue also yields the
-        # GroupNorm statistics block 0's norm1 needs)
-        cols = ops.im2col_rgb(x, 3, 1, 1, self._new(Fr * H * W, self.w['encoder.conv_in.weight'].shape[1]))
-        h = self._lin(cols, 'encoder.conv_in', a.ch, out=self._new(Fr, H, W, a.ch), gn_out=True)
+        # Cin = 3: the kernel builds the patch rows itself; its epilogue also yields block 0's GroupNorm statistics
+        h = self._new(Fr, H, W, a.ch)
+        stats = None
+        if self.fuse_gn_stats and (H * W) % 128 == 0 and a.ch == 64:
+            tpf = H * W // 128
+            stats = self._new(Fr * tpf * 4 * 64, dtype=torch.float32)
+            h._pgt_gn = (stats, tpf * 4)
+        ops.conv_rgb(x, self.w['encoder.conv_in.weight'], self.w['encoder.conv_in.bias'], h, 3, 1, 1, gn_stats=stats)
         feats = []
         for lvl in range(a.num_levels):
             last = lvl == a.num_levels - 1

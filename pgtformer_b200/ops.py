@@ -99,14 +99,15 @@ def conv(x, wp, cout, out, ksize=3, stride=1, pad_lo=1, bias=None, act=ACT_NONE,
     return out
 
 
-def im2col_rgb(x_nchw, ksize, stride, pad, out, mean3=None, std3=None):
-    """fp32 NCHW RGB -> bf16 [F*Ho*Wo, Kpad] patch matrix, K index (ky*ksize+kx)*3 + c; optional (x-mean)/std."""
+def conv_rgb(x_nchw, wp, bias, out, ksize, stride, pad, act=ACT_NONE, mean3=None, std3=None, gn_stats=None):
+    """Cin = 3 conv on the tensor cores straight from the fp32 NCHW image; wp [64, Kpad] bf16 (engine._pack_rgb)."""
     lib = L.load()
     F, C, H, W = x_nchw.shape
-    assert C == 3 and x_nchw.dtype == torch.float32 and x_nchw.is_contiguous() and out.is_contiguous()
+    assert C == 3 and x_nchw.dtype == torch.float32 and x_nchw.is_contiguous() and wp.dtype == torch.bfloat16
     m = (ctypes.c_float * 3)(*[float(v) for v in mean3]) if mean3 is not None else None
     s = (ctypes.c_float * 3)(*[float(v) for v in std3]) if std3 is not None else None
-    L.check(lib.pgt_im2col_rgb(_p(x_nchw), F, H, W, ksize, stride, pad, m, s, _p(out), out.shape[-1], _stream()))
+    L.check(lib.pgt_conv_rgb_bf16(_p(x_nchw), F, H, W, ksize, stride, pad, m, s, _p(wp), wp.stride(0), wp.shape[0],
+                                  _p(bias), act, _p(out), _rows(out)[2], _p(gn_stats), _stream()))
     return out
 
 

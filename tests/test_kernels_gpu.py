@@ -500,28 +500,32 @@ def test_conv_up2x_groupnorm_stats(Fr, H, W, C):
     check_close(out, gref, 'up2x fused-stats groupnorm', bf16_out=True, rel=3e-3)
 
 
-@pytest.mark.parametrize('ks,stride,pad,norm', [(3, 1, 1, False), (7, 2, 3, True)])
-def test_im2col_rgb_then_gemm(ks, stride, pad, norm):
-    """Cin = 3 convs (encoder conv_in, BiSeNet stem) as im2col + tensor-core GEMM: the patch matrix is bit-exact
-    against unfold on bf16-rounded inputs, the GEMM result matches conv2d."""
+@pytest.mark.parametrize('ks,stride,pad,norm,Fr,H,W', [(3, 1, 1, False, 3, 32, 48), (7, 2, 3, True, 3, 32, 48),
+                                                       (3, 1, 1, False, 2, 20, 36), (7, 2, 3, True, 5, 64, 64)])
+def test_conv_rgb_tensor_core(ks, stride, pad, norm, Fr, H, W):
+    """Cin = 3 convs (encoder conv_in, BiSeNet stem) with the im2col done inside the tcgen05 kernel; ragged last tile,
+    normalisation before the zero padding, fused GroupNorm statistics."""
     from pgtformer_b200.engine import _pack_rgb
     o = ops()
-    Fr, H, W = 3, 32, 48
     x = torch.rand(Fr, 3, H, W, generator=torch.Generator().manual_seed(180))
     mean, std = ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225)) if norm else (None, None)
     w, b = rnd((64, 3, ks, ks), 181, (3 * ks * ks) ** -0.5), rnd((64,), 182, 0.1)
-    wp = _pack_rgb(w.to(DEV))
     Ho, Wo = (H + 2 * pad - ks) // stride + 1, (W + 2 * pad - ks) // stride + 1
-    cols = torch.full((Fr * Ho * Wo, wp.shape[1]), 7.0, dtype=torch.bfloat16, device=DEV)
-    o.im2col_rgb(x.to(DEV), ks, stride, pad, cols, mean, std)
     xn = x if not norm else (x - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
-    u = F.unfold(xn, ks, padding=pad, stride=stride)                       # [F, 3*ks*ks (c-major), L]
-    u = u.view(Fr, 3, ks * ks, Ho * Wo).permute(0, 3, 2, 1).reshape(Fr * Ho * Wo, ks * ks * 3)
-    got = cols.float().cpu()
-    assert torch.all(got[:, 3 * ks * ks:] == 0)
-    # (x - mean) * (1 / std) vs (x - mean) / std differ by an fp32 ulp before the bf16 rounding
-    assert (got[:, :3 * ks * ks] - bf(u).float()).abs().max().item() <= (2 ** -6 if norm else 0.0)
+    act = o.ACT_RELU if norm else o.ACT_NONE
+    stats = None
+    if (Ho * Wo) % 128 == 0:
+        stats = torch.zeros(Fr * (Ho * Wo // 128) * 4 * 64, dtype=torch.float32, device=DEV)
     out = torch.empty(Fr, Ho, Wo, 64, dtype=torch.bfloat16, device=DEV)
-    o.linear(cols, wp, out, bias=b.to(DEV), N=64, act=o.ACT_RELU)
-    ref = F.relu(F.conv2d(bf(xn).float(), bf(w).float(), b, stride=stride, padding=pad)).permute(0, 2, 3, 1)
-    check_close(out, ref, 'rgb conv via im2col', bf16_out=True)
+    o.conv_rgb(x.to(DEV), _pack_rgb(w.to(DEV)), b.to(DEV), out, ks, stride, pad, act=act, mean3=mean, std3=std,
+               gn_stats=stats)
+    ref = F.conv2d(bf(xn).float(), bf(w).float(), b, stride=stride, padding=pad)
+    ref = (F.relu(ref) if norm else ref).permute(0, 2, 3, 1)
+    # (x - mean) * (1 / std) may round to the neighbouring bf16 of (x - mean) / std: a hair above pure bf16 output noise
+    check_close(out, ref, 'rgb conv', bf16_out=True, rel=6e-3 if norm else 1e-3)
+    if stats is not None:
+        gam, bet = 1 + 0.1 * rnd((64,), 183), 0.1 * rnd((64,), 184)
+        y = torch.empty_like(out)
+        o.groupnorm_apply_stats(out, gam.to(DEV), bet.to(DEV), y, stats, (Ho * Wo // 128) * 4)
+        gref = F.silu(F.group_norm(out.float().cpu().permute(0, 3, 1, 2), 32, gam, bet, eps=1e-6)).permute(0, 2, 3, 1)
+        check_close(y, gref, 'rgb conv fused-stats groupnorm', bf16_out=True, rel=3e-3)
