@@ -102,6 +102,16 @@ int pgt_linear_bf16(const void* A, int lda, const void* W, int ldw, int M, int N
 int pgt_conv_bf16(const void* x, int F, int Hin, int Win, int Cin, int ldx, const void* Wp, int ldw,
                   int Cout, int ksize, int stride, int pad_lo, const pgt_epilogue* ep, void* stream);
 
+/* ---- GroupNorm(32)+SiLU of the INPUT fused into the 3x3 / stride 1 / pad 1 conv: the normalised activation is never
+ * written to HBM — the kernel applies y = silu(x * a[f,c] + b[f,c]) to each input slab in shared memory (bit-identical
+ * to pgt_groupnorm_silu's apply pass) before the MMAs read it.  gn_ab: fp32 [F][2][Cin] from pgt_groupnorm_ab.
+ * Available where the halo-reuse kernel is (pgt_conv_gn_supported: Cout <= 128, Hin >= 16, Win >= 8, Cin % 8 == 0);
+ * PGT_ERR_UNSUPPORTED otherwise.  Replaces  Normalize -> swish -> conv  of TDResnetBlock (modules/rstt_layers.py:
+ * 875-904), ResBlock (archs/pgtformer_arch.py:421-432) and norm_out -> conv_out (archs/tdcrqvae3_arch.py:569-572). */
+int pgt_conv_gn_supported(int Hin, int Win, int Cin, int Cout);
+int pgt_conv_gn_bf16(const void* x, int F, int Hin, int Win, int Cin, int ldx, const float* gn_ab, const void* Wp,
+                     int ldw, int Cout, const pgt_epilogue* ep, void* stream);
+
 /* ---- nearest-x2 upsample + 3x3 conv as ONE op, without materialising the upsampled tensor: the output
  * pixel (2y+py, 2x+px) only sees a 2x2 neighbourhood of the source, so the op is four 2x2 convolutions
  * (one per output phase) over the SOURCE resolution with tap-summed weights: 4/9 of the FLOPs, 1/4 of the
@@ -144,6 +154,12 @@ int pgt_conv_tiles_per_frame(int Hin, int Win, int Cout, int ksize, int stride, 
 int pgt_groupnorm_apply_stats(const void* x, int ldx, int F, int HW, int C, const float* gamma, const float* beta,
                               float eps, int apply_silu, void* y, int ldy, const float* stats, int chunks_per_frame,
                               float* ws, void* stream);
+
+/* GroupNorm statistics -> per-(frame, channel) affine terms only: ab[f][0][c] = rstd*gamma, ab[f][1][c] = beta -
+ * mean*rstd*gamma (fp32 [F][2][C]), for pgt_conv_gn_bf16.  stats/chunks_per_frame as in pgt_groupnorm_apply_stats, or
+ * stats == NULL to compute them from x (ws: pgt_groupnorm_ws_floats floats). */
+int pgt_groupnorm_ab(const void* x, int ldx, int F, int HW, int C, const float* gamma, const float* beta, float eps,
+                     const float* stats, int chunks_per_frame, float* ws, float* ab, void* stream);
 int pgt_groupnorm_silu(const void* x, int ldx, int F, int HW, int C, const float* gamma, const float* beta,
                        float eps, int apply_silu, void* y, int ldy, float* ws, void* stream);
 

@@ -36,6 +36,7 @@ constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32 + 32;     // TMA producer, MMA 
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int PANEL_BYTES = BM * 128;            // one staging panel: 128 rows x 128 B
 constexpr int NUM_SLOTS = 4;                     // staging slots (two per epilogue half-group)
+constexpr int PREFETCH_TILES = 2;                // L2 prefetch distance of the TMA producers, in rounds of gridDim tiles
 
 enum { MODE_LINEAR = 0, MODE_CONV_S1 = 1, MODE_CONV_S2 = 2 };
 
@@ -57,6 +58,8 @@ struct GemmParams {
   int act, epi_mode;
   float* gn_stats;       // optional: per-(tile, group) partial (sum, sumsq) of the OUTPUT for the next GroupNorm(32)
   int gn_cpg;            // channels per group = N / 32
+  const float* gn_ab;    // halo conv only: GroupNorm+SiLU of the INPUT applied to the slab in smem, [F][2][gn_c] (a, b)
+  int gn_c;              //   channels of that GroupNorm (= Cin)
   int gn_tpf;            // > 0: statistics rows are laid out [frame][gn_fstride] (several launches share one buffer)
   int gn_fstride;        //      chunk = (m_blk / gn_tpf) * gn_fstride + (m_blk % gn_tpf) * 4 + quad
   int relu_after_res;    // ResNet BasicBlock: out = relu(conv + shortcut) — ReLU applied after the residual add
@@ -556,23 +559,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
-            const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES));
+        // one elected lane walks the whole k loop of the tile (waits included): a per-k-block elect region costs
+        // ~70 issue slots of descriptor / uniform-register setup, more than the MMAs of a narrow tile take
+        if (elect_one()) {
+          int s = stage;
+          uint32_t ph = phase;
+          const uint64_t da0 = umma_desc_k_sw128(smem_u32(smem_a));
+          const uint64_t db0 = umma_desc_k_sw128(smem_u32(smem_b));
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint64_t da = da0 + (uint64_t)(s * (A_STAGE_BYTES >> 4));
+            const uint64_t db = db0 + (uint64_t)(s * (Cfg::B_STAGE_BYTES >> 4));
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               // +32 bytes (2 x 16 B units) per UMMA_K=16 step inside the 128 B swizzle row
               umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            umma_commit(&empty_bar[stage]);              // frees the smem stage when the MMAs retire
-            if (kb == p.num_kb - 1) umma_commit(&tmem_full[acc]);
+            umma_commit(&empty_bar[s]);                  // frees the smem stage when the MMAs retire
+            if (++s == STAGES) { s = 0; ph ^= 1; }
           }
-          __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          umma_commit(&tmem_full[acc]);
         }
+        __syncwarp();
+        const int ns = stage + p.num_kb;
+        phase ^= (ns / STAGES) & 1;
+        stage = ns % STAGES;
       }
     }
   } else if (warp < 2 + EPI_WARPS) {
@@ -629,8 +641,10 @@ struct HaloCfg {
   static_assert(SMEM_BYTES <= 232448, "halo conv smem budget");
 };
 
-template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+constexpr int HALO_GN_THREADS = 128;             // extra warps of the GroupNorm-fused variant
+
+template <int BN, bool GN>
+__global__ void __launch_bounds__(GN ? GEMM_THREADS + HALO_GN_THREADS : GEMM_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                  const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
@@ -651,6 +665,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* res_bar = tmem_full + 4;                                   // [NUM_SLOTS]
   uint64_t* slot_ready = tmem_full + 8;                                // [NUM_SLOTS]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 12);
+  uint64_t* a_ready = tmem_full + 14;                                  // [AS] GN variant: slab normalised in place
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -663,7 +678,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (p.fast_epi) tma_prefetch_desc(&tmO);
     if (p.has_res_map) tma_prefetch_desc(&tmR);
     if (p.fast_epi && p.epi_mode == PGT_EPI_SFT) tma_prefetch_desc(&tmX);
-    for (int i = 0; i < AS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < AS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], HALO_GN_THREADS); }
     for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -692,6 +707,25 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int m_blk = tile / p.n_tiles;
       int n0, y0, x0;
       decode_conv_tile(p, m_blk, n0, y0, x0);
+      {
+        // pull the slab (and residual panels) of the tile PREFETCH_TILES rounds ahead into L2: three slabs in flight per
+        // SM do not cover the HBM latency of the 512^2 / 256^2 layers
+        const int pt = tile + PREFETCH_TILES * (int)gridDim.x;
+        if (BN == 64 && pt < num_tiles && elect_one()) {      // measured: helps the 64-wide layers only
+          int pn0, py0, px0;
+          decode_conv_tile(p, pt / p.n_tiles, pn0, py0, px0);
+          for (int cb = 0; cb < p.cin_blocks; ++cb) tma_prefetch_4d(&tmA, cb * BK, px0 - 1, py0 - 1, pn0);
+          if (p.has_res_map) {
+            const int c0 = (pt % p.n_tiles) * BN;
+            const int rw = p.out_dtype == PGT_BF16 ? 64 : 32;
+            for (int c = 0; c < BN && c0 + c < p.N; c += rw) {
+              tma_prefetch_4d(&tmR, c0 + c, px0, py0, pn0);
+              if (p.epi_mode == PGT_EPI_SFT) tma_prefetch_4d(&tmX, c0 + c, px0, py0, pn0);
+            }
+          }
+        }
+        __syncwarp();
+      }
       for (int cb = 0; cb < p.cin_blocks; ++cb) {
         mbar_wait(&a_empty[as], aph ^ 1);
         if (elect_one()) {
@@ -724,36 +758,120 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
-      uint32_t accumulate = 0;
-      for (int cb = 0; cb < p.cin_blocks; ++cb) {
-        mbar_wait(&a_full[as], aph);
-        const uint32_t a_addr = smem_u32(smem_a + as * HALO_A_STRIDE);
-        for (int t = 0; t < 9; ++t) {
-          if (!p.b_resident || it == 0) mbar_wait(&b_full[bs], bph);
-          tc_fence_after();
-          if (elect_one()) {
-            const int dy = t / 3, dx = t - 3 * dy;
-            const uint64_t da = umma_desc_k_sw128_sbo(a_addr + (dy * (HALO_TW + 2) + dx) * 128, HALO_PITCH);
-            const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + bs * Cfg::B_BYTES));
+      // one elected lane issues the whole tile (nine taps x four k-steps per channel block, tap offsets are
+      // compile-time constants): per-tap elect regions cost more issue slots than the MMAs of a 64-wide tile take
+      if (elect_one()) {
+        int a = as, b = bs;
+        uint32_t ap = aph, bp = bph;
+        const uint64_t da_base = umma_desc_k_sw128_sbo(smem_u32(smem_a), HALO_PITCH);
+        const uint64_t db_base = umma_desc_k_sw128(smem_u32(smem_b));
+        for (int cb = 0; cb < p.cin_blocks; ++cb) {
+          mbar_wait(GN ? &a_ready[a] : &a_full[a], ap);
+          const uint64_t da0 = da_base + (uint64_t)(a * (HALO_A_STRIDE >> 4));
+          if (p.b_resident) {
+            if (it == 0) {
+              for (int t = 0; t < 9; ++t) mbar_wait(&b_full[t], 0);
+            }
+            tc_fence_after();
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (accumulate | k) != 0 ? 1u : 0u);
-            if (!p.b_resident) umma_commit(&b_empty[bs]);
-            if (t == 8) umma_commit(&a_empty[as]);
-            if (t == 8 && cb == p.cin_blocks - 1) umma_commit(&tmem_full[acc]);
+            for (int t = 0; t < 9; ++t) {
+              const uint64_t da = da0 + (uint64_t)(((t / 3) * (HALO_TW + 2) + (t % 3)) * 8);
+              const uint64_t db = db_base + (uint64_t)(t * (Cfg::B_BYTES >> 4));
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (cb | t | k) != 0 ? 1u : 0u);
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              mbar_wait(&b_full[b], bp);
+              tc_fence_after();
+              const uint64_t da = da0 + (uint64_t)(((t / 3) * (HALO_TW + 2) + (t % 3)) * 8);
+              const uint64_t db = db_base + (uint64_t)(b * (Cfg::B_BYTES >> 4));
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (cb | t | k) != 0 ? 1u : 0u);
+              umma_commit(&b_empty[b]);
+              if (++b == BS) { b = 0; bp ^= 1; }
+            }
           }
-          __syncwarp();
-          accumulate = 1;
-          if (++bs == BS) { bs = 0; bph ^= 1; }
+          umma_commit(&a_empty[a]);
+          if (++a == AS) { a = 0; ap ^= 1; }
         }
-        if (++as == AS) { as = 0; aph ^= 1; }
+        umma_commit(&tmem_full[acc]);
+      }
+      __syncwarp();
+      {
+        const int na = as + p.cin_blocks;
+        aph ^= (na / AS) & 1;
+        as = na % AS;
+        if (!p.b_resident) {
+          const int nb = bs + 9 * p.cin_blocks;
+          bph ^= (nb / BS) & 1;
+          bs = nb % BS;
+        }
       }
     }
   } else if (warp < 2 + EPI_WARPS) {
     EpiCtx ctx{staging, tmem_full, tmem_empty, res_bar, slot_ready, tmem_base};
     epilogue_loop<BN>(p, ctx, warp, lane, num_tiles);
-  } else {
+  } else if (warp == 2 + EPI_WARPS) {
     EpiCtx ctx{staging, tmem_full, tmem_empty, res_bar, slot_ready, tmem_base};
     epilogue_dma_loop<BN>(p, ctx, tmO, tmR, tmX, lane, num_tiles);
+  } else if (GN) {
+    // ------------------------------------------------------------------ GroupNorm + SiLU of the input, in the slab
+    // y = silu(x * a[f,c] + b[f,c]) exactly as gn_apply_kernel computes it, applied to every in-image pixel of the
+    // slab once it has landed (the zero padding TMA wrote for out-of-image pixels must stay zero), then handed to the
+    // MMA lane through a_ready.  Thread = one 16-byte channel chunk column (fixed 8 channels) x every 16th pixel row.
+    const int t = threadIdx.x - GEMM_THREADS;
+    const int c = t & 7, rl = t >> 3;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int n0, y0, x0;
+      decode_conv_tile(p, tile / p.n_tiles, n0, y0, x0);
+      for (int cb = 0; cb < p.cin_blocks; ++cb) {
+        float ah[8], bh[8];
+        const int ch0 = cb * BK + c * 8;
+        if (ch0 < p.gn_c) {
+          const float4* pa = reinterpret_cast<const float4*>(p.gn_ab + ((size_t)n0 * 2 + 0) * p.gn_c + ch0);
+          const float4* pb = reinterpret_cast<const float4*>(p.gn_ab + ((size_t)n0 * 2 + 1) * p.gn_c + ch0);
+          const float4 a0 = __ldg(pa), a1 = __ldg(pa + 1), b0 = __ldg(pb), b1 = __ldg(pb + 1);
+          ah[0] = a0.x; ah[1] = a0.y; ah[2] = a0.z; ah[3] = a0.w; ah[4] = a1.x; ah[5] = a1.y; ah[6] = a1.z; ah[7] = a1.w;
+          bh[0] = b0.x; bh[1] = b0.y; bh[2] = b0.z; bh[3] = b0.w; bh[4] = b1.x; bh[5] = b1.y; bh[6] = b1.z; bh[7] = b1.w;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { ah[j] *= 0.5f; bh[j] *= 0.5f; }     // silu(v) = h + h tanh(h), h = v / 2
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { ah[j] = 0.f; bh[j] = 0.f; }         // channel padding stays zero
+        }
+        mbar_wait(&a_full[as], aph);
+        uint8_t* slab = smem_a + as * HALO_A_STRIDE;
+#pragma unroll 4
+        for (int j = 0; j < 12; ++j) {
+          const int r = rl + 16 * j;
+          if (r >= (HALO_TH + 2) * (HALO_TW + 2)) break;
+          const int sy = r / (HALO_TW + 2), sx = r - sy * (HALO_TW + 2);
+          if ((unsigned)(y0 - 1 + sy) >= (unsigned)p.H || (unsigned)(x0 - 1 + sx) >= (unsigned)p.W) continue;
+          uint4* ptr = reinterpret_cast<uint4*>(slab + r * 128 + ((c ^ (r & 7)) << 4));
+          const uint4 u = *ptr;
+          const float2 q0 = unpack_bf16x2(u.x), q1 = unpack_bf16x2(u.y), q2 = unpack_bf16x2(u.z), q3 = unpack_bf16x2(u.w);
+          float v[8] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float h = fmaf(v[e], ah[e], bh[e]);
+            float th;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+            v[e] = fmaf(h, th, h);
+          }
+          uint4 o;
+          o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+          o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+          *ptr = o;
+        }
+        fence_proxy_async();
+        mbar_arrive(&a_ready[as]);
+        if (++as == AS) { as = 0; aph ^= 1; }
+      }
+    }
   }
 
   tc_fence_before();
@@ -900,7 +1018,7 @@ static int launch_gemm(const CUtensorMap& tmA, const void* W, int ldw, GemmParam
   return PGT_OK;
 }
 
-template <int BN>
+template <int BN, bool GN>
 static int launch_halo(const CUtensorMap& tmA, const void* W, int ldw, GemmParams& p, cudaStream_t stream) {
   using Cfg = HaloCfg<BN>;
   CUtensorMap tmB, tmO, tmR, tmX;
@@ -912,7 +1030,7 @@ static int launch_halo(const CUtensorMap& tmA, const void* W, int ldw, GemmParam
   p.b_resident = (9 * p.cin_blocks == Cfg::B_STAGES && p.n_tiles == 1) ? 1 : 0;
   static bool attr_set = false;
   if (!attr_set) {
-    PGT_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    PGT_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<BN, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
@@ -920,9 +1038,11 @@ static int launch_halo(const CUtensorMap& tmA, const void* W, int ldw, GemmParam
   {
     char desc[96];
     if (prof_enabled())
-      snprintf(desc, sizeof(desc), "halo3 F%d H%d W%d K%d N%d BN%d e%d r%d", p.F, p.H, p.W, p.K, p.N, BN, p.fast_epi, p.b_resident);
+      snprintf(desc, sizeof(desc), "halo3%s F%d H%d W%d K%d N%d BN%d e%d r%d", GN ? "+gn" : "", p.F, p.H, p.W, p.K, p.N, BN,
+               p.fast_epi, p.b_resident);
     ProfScope ps(PGT_PROF_GEMM, p.flops, stream, desc);
-    conv_halo_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, tmR, tmX, p);
+    conv_halo_kernel<BN, GN><<<grid, GN ? GEMM_THREADS + HALO_GN_THREADS : GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(
+        tmA, tmB, tmO, tmR, tmX, p);
   }
   PGT_LAUNCH_OK();
   return PGT_OK;
@@ -997,7 +1117,8 @@ extern "C" int pgt_linear_bf16(const void* A, int lda, const void* W, int ldw, i
 // pad_y/pad_x: zero rows/cols before the input (stride 1); up_phase >= 0: phase (py = up_phase>>1, px = up_phase&1)
 // of a nearest-x2-upsample-folded conv — the [F,Hin,Win,Cout] result is scattered to out[F, 2y+py, 2x+px, :].
 static int conv_impl(const void* x, int F, int Hin, int Win, int Cin, int ldx, const void* Wp, int ldw, int Cout,
-                     int ksize, int stride, int pad_y, int pad_x, int up_phase, const pgt_epilogue* ep, void* stream) {
+                     int ksize, int stride, int pad_y, int pad_x, int up_phase, const pgt_epilogue* ep, void* stream,
+                     const float* gn_ab = nullptr) {
   const int pad_lo = pad_y;
   PGT_CHECK_ARG(x && Wp && F > 0 && Hin > 0 && Win > 0 && Cin > 0 && Cout > 0);
   PGT_CHECK_ARG((ksize >= 1 && ksize <= 3) && (stride == 1 || stride == 2) && pad_y >= 0 && pad_y <= 1 && pad_x >= 0 && pad_x <= 1);
@@ -1069,7 +1190,12 @@ static int conv_impl(const void* x, int F, int Hin, int Win, int Cin, int ldx, c
     rc = encode_map(&tmA, x, 4, dims, str, box);
     if (rc == PGT_OK && halo) {
       cudaStream_t st = static_cast<cudaStream_t>(stream);
-      return Cout <= 64 ? launch_halo<64>(tmA, Wp, ldw, p, st) : launch_halo<128>(tmA, Wp, ldw, p, st);
+      if (gn_ab != nullptr) {
+        p.gn_ab = gn_ab;
+        p.gn_c = Cin;
+        return Cout <= 64 ? launch_halo<64, true>(tmA, Wp, ldw, p, st) : launch_halo<128, true>(tmA, Wp, ldw, p, st);
+      }
+      return Cout <= 64 ? launch_halo<64, false>(tmA, Wp, ldw, p, st) : launch_halo<128, false>(tmA, Wp, ldw, p, st);
     }
   } else {
     uint64_t dims[5] = {(uint64_t)2 * ldx, (uint64_t)Win / 2, 2, (uint64_t)Hin / 2, (uint64_t)F};
@@ -1079,6 +1205,7 @@ static int conv_impl(const void* x, int F, int Hin, int Win, int Cin, int ldx, c
     rc = encode_map(&tmA, x, 5, dims, str, box);
   }
   if (rc != PGT_OK) return rc;
+  if (gn_ab != nullptr) return PGT_ERR_UNSUPPORTED;          // the fused input GroupNorm exists on the halo path only
   if (up_phase >= 0) {
     // strided placement exists only on the TMA-store path
     const int esz = p.out_dtype == PGT_BF16 ? 2 : 4;
@@ -1107,6 +1234,18 @@ extern "C" int pgt_conv_bf16(const void* x, int F, int Hin, int Win, int Cin, in
                              int Cout, int ksize, int stride, int pad_lo, const pgt_epilogue* ep, void* stream) {
   PGT_CHECK_ARG(ksize == 1 || ksize == 3);
   return conv_impl(x, F, Hin, Win, Cin, ldx, Wp, ldw, Cout, ksize, stride, pad_lo, pad_lo, -1, ep, stream);
+}
+
+extern "C" int pgt_conv_gn_supported(int Hin, int Win, int Cin, int Cout) {
+  static const bool no_halo = getenv("PGT_NO_HALO") != nullptr;
+  return (!no_halo && Cout <= 128 && Hin >= HALO_TH && Win >= HALO_TW && Cin % 8 == 0) ? 1 : 0;
+}
+
+extern "C" int pgt_conv_gn_bf16(const void* x, int F, int Hin, int Win, int Cin, int ldx, const float* gn_ab, const void* Wp,
+                                int ldw, int Cout, const pgt_epilogue* ep, void* stream) {
+  PGT_CHECK_ARG(gn_ab != nullptr && Cin % 8 == 0);
+  if (!pgt_conv_gn_supported(Hin, Win, Cin, Cout)) return PGT_ERR_UNSUPPORTED;
+  return conv_impl(x, F, Hin, Win, Cin, ldx, Wp, ldw, Cout, 3, 1, 1, 1, -1, ep, stream, gn_ab);
 }
 
 extern "C" int pgt_conv_up2x_bf16(const void* x, int F, int Hin, int Win, int Cin, int ldx, const void* Wp4, int ldw,

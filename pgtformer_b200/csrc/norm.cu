@@ -393,6 +393,29 @@ extern "C" int pgt_groupnorm_apply_stats(const void* x, int ldx, int F, int HW, 
   return PGT_OK;
 }
 
+// finalize only: per-(frame, channel) affine terms for a consumer that applies the normalisation itself
+extern "C" int pgt_groupnorm_ab(const void* x, int ldx, int F, int HW, int C, const float* gamma, const float* beta,
+                                float eps, const float* stats, int chunks_per_frame, float* ws, float* ab, void* stream) {
+  PGT_CHECK_ARG(gamma && beta && ab && F > 0 && HW > 0 && C % 32 == 0 && C / 8 <= GN_APPLY_THREADS);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (stats != nullptr) {
+    PGT_CHECK_ARG(chunks_per_frame > 0);
+    gn_finalize_kernel<<<F, GN_FIN_PARTS * 32, 0, st>>>(stats, chunks_per_frame, HW, C, gamma, beta, eps, ab);
+    PGT_LAUNCH_OK();
+    return PGT_OK;
+  }
+  PGT_CHECK_ARG(x && ws && ldx % 8 == 0);
+  ProfScope ps(PGT_PROF_NORM, 1.0 * F * (double)HW * C * 2, st, "gn_stats");
+  const int nchunks = gn_chunks(HW);
+  const int ppc = ceil_div(HW, nchunks);
+  const size_t stats_smem = ((size_t)(GN_THREADS / (C / 8)) + 1) * 2 * C * sizeof(float);
+  gn_stats_kernel<<<dim3(nchunks, F), GN_THREADS, stats_smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C, ppc, ws);
+  PGT_LAUNCH_OK();
+  gn_finalize_kernel<<<F, GN_FIN_PARTS * 32, 0, st>>>(ws, nchunks, HW, C, gamma, beta, eps, ab);
+  PGT_LAUNCH_OK();
+  return PGT_OK;
+}
+
 extern "C" int pgt_layernorm(const void* x, int ldx, int x_dtype, int T, int C, const float* gamma, const float* beta,
                              float eps, void* y, int ldy, const void* pos, int ldpos, void* y2, int ldy2,
                              void* stream) {

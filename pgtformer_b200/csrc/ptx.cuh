@@ -85,6 +85,16 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
 }
 
 // TMA stores (shared -> global, bulk async-group completion); out-of-bounds parts of the box are clipped.
+// L2 prefetch of a tensor-map box (no smem, no barrier): issued a few tiles ahead so the later smem load is an L2 hit
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(m), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(m), "r"(c0), "r"(c1), "r"(c2),
+               "r"(c3)
+               : "memory");
+}
+
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),

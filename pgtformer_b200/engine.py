@@ -120,6 +120,10 @@ class Engine:
         return torch.empty(*shape, dtype=dtype, device=self.dev)
 
     fuse_swin_mlp = True      # LN + fc1 + GELU + fc2 + residual of the C=256 Swin blocks as one kernel
+    # GroupNorm+SiLU applied inside the consuming 3x3 conv (pgt_conv_gn_bf16, bit-identical).  Off by default: the
+    # narrow (Cout <= 128) halo convs are bound by shared-memory operand reads, so the in-place slab transform costs
+    # them more (+10 ms at 16 clips of 512^2) than the GroupNorm apply passes it removes (-6.8 ms); see DESIGN.md.
+    fuse_gn_apply = False
     fuse_gn_stats = True      # GroupNorm statistics from the producing conv / linear epilogue (saves one pass)
 
     def _gn(self, x, p, silu=True):
@@ -129,9 +133,21 @@ class Engine:
                                              silu=silu)
         return ops.groupnorm_silu(x, self.w[p + '.weight'], self.w[p + '.bias'], self._new(*x.shape), silu=silu)
 
-    def _conv3(self, x, p, cout, out=None, gn_out=False, **kw):
-        Fr, H, W, _ = x.shape
+    def _conv3(self, x, p, cout, out=None, gn_out=False, gn=None, **kw):
+        """3x3 conv; gn: name of the Normalize() whose GroupNorm+SiLU precedes it — applied inside the conv kernel
+        where the halo path exists (the normalised tensor never reaches HBM), as a separate pass otherwise."""
+        Fr, H, W, cin = x.shape
         stride = kw.get('stride', 1)
+        fused_ab = None
+        if gn is not None:
+            if self.fuse_gn_apply and stride == 1 and kw.get('ksize', 3) == 3 and kw.get('pad_lo', 1) == 1 and \
+                    'act' not in kw and not kw.get('relu_after_res') and ops.conv_gn_supported(H, W, cin, cout):
+                st = getattr(x, '_pgt_gn', None)
+                fused_ab = ops.groupnorm_ab(x, self.w[gn + '.weight'], self.w[gn + '.bias'],
+                                            self._new(Fr * 2 * cin, dtype=torch.float32),
+                                            stats=st[0] if st else None, chunks_per_frame=st[1] if st else 0)
+            else:
+                x = self._gn(x, gn)
         if out is None:
             out = self._new(Fr, H // stride, W // stride, cout)
         stats = None
@@ -140,6 +156,10 @@ class Engine:
             if tpf > 0:
                 stats = self._new(Fr * tpf * 4 * 64, dtype=torch.float32)      # [tile][TMEM quadrant][32 groups][2]
                 out._pgt_gn = (stats, tpf * 4)
+        if fused_ab is not None:
+            kw.pop('ksize', None); kw.pop('stride', None); kw.pop('pad_lo', None)
+            return ops.conv_gn(x, fused_ab, self.w[p + '.weight'], cout, out, bias=self.w.get(p + '.bias'),
+                               gn_stats=stats, **kw)
         return ops.conv(x, self.w[p + '.weight'], cout, out, bias=self.w.get(p + '.bias'), gn_stats=stats, **kw)
 
     def _lin(self, x, p, n, out=None, out_dtype=BF, gn_out=False, **kw):
@@ -158,9 +178,9 @@ class Engine:
         """TDResnetBlock (`modules/rstt_layers.py:875-904`): 2 x (GN+SiLU -> conv3x3), residual in the
         second conv's epilogue (1x1 nin_shortcut first when the width changes).  conv1's epilogue also emits the
         GroupNorm statistics norm2 needs; with gn_next the block output carries them for the next Normalize()."""
-        h = self._conv3(self._gn(x, p + '.norm1'), p + '.conv1', cout, gn_out=True)
+        h = self._conv3(x, p + '.conv1', cout, gn=p + '.norm1', gn_out=True)
         sc = self._lin(x, p + '.nin_shortcut', cout) if (p + '.nin_shortcut.weight') in self.w else x
-        return self._conv3(self._gn(h, p + '.norm2'), p + '.conv2', cout, residual=sc, gn_out=gn_next)
+        return self._conv3(h, p + '.conv2', cout, gn=p + '.norm2', residual=sc, gn_out=gn_next)
 
     def swin_block(self, x, p, heads, shift, gn_next=False):
         """VSTSREncoderTransformerBlock (`modules/rstt_layers.py:284-338`) on [F,H,W,C]."""
@@ -206,9 +226,9 @@ class Engine:
         fut = ops.regroup_frames(self._lin(tcat, p + '.tfusion0', 96), self._new(Fr, P, 32), b, P, 32, 1)
         self._lin(fut, p + '.tfusion1', 32, out=cat.view(Fr, P, 2 * C + 32)[..., 2 * C:])
         e = p + '.encode_enc'
-        h = self._conv3(self._gn(cat, e + '.norm1'), e + '.conv1', C, gn_out=True)
+        h = self._conv3(cat, e + '.conv1', C, gn=e + '.norm1', gn_out=True)
         sc = self._lin(cat, e + '.conv_out', C)
-        ef = self._conv3(self._gn(h, e + '.norm2'), e + '.conv2', C, residual=sc)
+        ef = self._conv3(h, e + '.conv2', C, gn=e + '.norm2', residual=sc)
         scale = self._conv3(self._conv3(ef, p + '.scale.0', C, act=ops.ACT_LRELU02), p + '.scale.2', C)
         sh = self._conv3(ef, p + '.shift.0', C, act=ops.ACT_LRELU02)
         return self._conv3(sh, p + '.shift.2', C, residual=dec, sft_scale=scale, sft_w=wgt, gn_out=gn_next)
@@ -356,7 +376,7 @@ class Engine:
         h = self.encoder_layer(h, 'encoder.mid.attn_1', a.num_heads[-1], a.depths[-1], gn_next=True)
         h = self.td_resblock(h, 'encoder.mid.block_2', a.level_ch[-1], gn_next=True)
         zc = 2 * a.z_channels if a.double_z else a.z_channels
-        return self._conv3(self._gn(h, 'encoder.norm_out'), 'encoder.conv_out', zc), feats
+        return self._conv3(h, 'encoder.conv_out', zc, gn='encoder.norm_out'), feats
 
     def decoder(self, z, feats=None, wgt=0.0):
         """Decoder.forward (`archs/tdcrqvae3_arch.py:672-707`) / the inlined variant with SFT fusion
@@ -392,7 +412,7 @@ class Engine:
                 h = ops.conv_up2x(h, self.w[p + '.weight'], C, out, bias=self.w[p + '.bias'], gn_stats=stats)
         Fr, H, W, _ = h.shape
         out = self._new(Fr, a.out_ch, H, W, dtype=torch.float32)
-        self._conv3(self._gn(h, 'decoder.norm_out'), 'decoder.conv_out', a.out_ch, out=out, nchw=True)
+        self._conv3(h, 'decoder.conv_out', a.out_ch, out=out, gn='decoder.norm_out', nchw=True)
         return out
 
     def parse_pos(self, x):

@@ -173,6 +173,43 @@ def groupnorm_apply_stats(x, gamma, beta, out, stats, chunks_per_frame, eps=1e-6
     return out
 
 
+def groupnorm_ab(x, gamma, beta, ab, stats=None, chunks_per_frame=0, eps=1e-6):
+    """Per-(frame, channel) GroupNorm affine terms ab [F, 2, C] fp32 (for conv_gn), from fused statistics or from x."""
+    lib = L.load()
+    F = x.shape[0]
+    C = x.shape[-1]
+    HW = x.shape[1] * x.shape[2]
+    ws = None
+    if stats is None:
+        n = lib.pgt_groupnorm_ws_floats(F, HW, C)
+        key = (x.device.index, torch.cuda.current_stream().cuda_stream)
+        ws = _gn_ws.get(key)
+        if ws is None or ws.numel() < n:
+            ws = torch.empty(max(n, 1 << 16), dtype=torch.float32, device=x.device)
+            _gn_ws[key] = ws
+    assert ab.dtype == torch.float32 and ab.numel() >= F * 2 * C and ab.is_contiguous()
+    L.check(lib.pgt_groupnorm_ab(_p(x), _rows(x)[2], F, HW, C, _p(gamma), _p(beta), eps, _p(stats), chunks_per_frame,
+                                 _p(ws), _p(ab), _stream()))
+    return ab
+
+
+def conv_gn_supported(H, W, cin, cout):
+    return bool(L.load().pgt_conv_gn_supported(H, W, cin, cout))
+
+
+def conv_gn(x, ab, wp, cout, out, bias=None, act=ACT_NONE, residual=None, sft_scale=None, sft_w=0.0, nchw=False,
+            gn_stats=None):
+    """conv3x3(silu(groupnorm(x))) with the normalisation applied to the input slabs in shared memory."""
+    lib = L.load()
+    F, H, W, Cin = x.shape
+    assert x.dtype == torch.bfloat16 and x.stride(3) == 1 and x.stride(1) == W * x.stride(2) and \
+        (F == 1 or x.stride(0) == H * x.stride(1))
+    ep = make_epilogue(out, bias, act, residual, sft_scale, sft_w, nchw, False, gn_stats)
+    L.check(lib.pgt_conv_gn_bf16(_p(x), F, H, W, Cin, x.stride(2), _p(ab), _p(wp), wp.stride(0), cout,
+                                 ctypes.byref(ep), _stream()))
+    return out
+
+
 def layernorm(x, gamma, beta, out, eps=1e-5, pos=None, out2=None):
     lib = L.load()
     T, C, ldx = _rows(x)
