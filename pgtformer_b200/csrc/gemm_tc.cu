@@ -58,6 +58,7 @@ struct GemmParams {
   int act, epi_mode;
   float* gn_stats;       // optional: per-(tile, group) partial (sum, sumsq) of the OUTPUT for the next GroupNorm(32)
   int gn_cpg;            // channels per group = N / 32
+  int ntaps, tap_kw, tap_oy, tap_ox;   // halo conv: 9 taps of a 3x3, or the 4 taps (kw = 2) of an upsample phase at slab offset (oy, ox)
   const float* gn_ab;    // halo conv only: GroupNorm+SiLU of the INPUT applied to the slab in smem, [F][2][gn_c] (a, b)
   int gn_c;              //   channels of that GroupNorm (= Cin)
   int gn_tpf;            // > 0: statistics rows are laid out [frame][gn_fstride] (several launches share one buffer)
@@ -129,6 +130,7 @@ struct EpiCtx {
   uint64_t* res_bar;       // [NUM_SLOTS] staging slot prepared (free, residual landed)   DMA warp -> epilogue
   uint64_t* slot_ready;    // [NUM_SLOTS] staging slot holds the finished panel           epilogue -> DMA warp
   uint32_t tmem_base;
+  uint32_t tmem_empty_cluster;   // != 0: shared::cluster address of the pair leader's tmem_empty[0] (2-CTA kernels)
 };
 
 // One 32-column chunk of a staging panel: TMEM -> +bias -> act -> (+residual | SFT) -> packed into the swizzled row.
@@ -447,7 +449,12 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, const EpiCtx&
       }
     }
     tc_fence_before();
-    mbar_arrive(&tmem_empty[acc]);
+    if (ctx.tmem_empty_cluster != 0) {
+      __syncwarp();                                   // one cluster-scope arrive per warp, not per thread
+      if (lane == 0) mbar_arrive_cluster(ctx.tmem_empty_cluster + acc * 8);
+    } else {
+      mbar_arrive(&tmem_empty[acc]);
+    }
   }
 }
 
@@ -735,7 +742,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         __syncwarp();
         if (++as == AS) { as = 0; aph ^= 1; }
         if (p.b_resident && tile != (int)blockIdx.x) continue;   // weights already resident in the ring
-        for (int t = 0; t < 9; ++t) {
+        for (int t = 0; t < p.ntaps; ++t) {
           mbar_wait(&b_empty[bs], bph ^ 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(&b_full[bs], Cfg::B_BYTES);
@@ -770,22 +777,44 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t da0 = da_base + (uint64_t)(a * (HALO_A_STRIDE >> 4));
           if (p.b_resident) {
             if (it == 0) {
-              for (int t = 0; t < 9; ++t) mbar_wait(&b_full[t], 0);
+              for (int t = 0; t < p.ntaps; ++t) mbar_wait(&b_full[cb * p.ntaps + t], 0);
             }
             tc_fence_after();
+            if (p.ntaps == 9) {
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-              const uint64_t da = da0 + (uint64_t)(((t / 3) * (HALO_TW + 2) + (t % 3)) * 8);
-              const uint64_t db = db_base + (uint64_t)(t * (Cfg::B_BYTES >> 4));
+              for (int t = 0; t < 9; ++t) {
+                const uint64_t da = da0 + (uint64_t)(((t / 3) * (HALO_TW + 2) + (t % 3)) * 8);
+                const uint64_t db = db_base + (uint64_t)((cb * 9 + t) * (Cfg::B_BYTES >> 4));
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (cb | t | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (cb | t | k) != 0 ? 1u : 0u);
+              }
+            } else {
+              for (int t = 0; t < p.ntaps; ++t) {
+                const int dy = t / p.tap_kw, dx = t - dy * p.tap_kw;
+                const uint64_t da = da0 + (uint64_t)(((dy + p.tap_oy) * (HALO_TW + 2) + dx + p.tap_ox) * 8);
+                const uint64_t db = db_base + (uint64_t)((cb * p.ntaps + t) * (Cfg::B_BYTES >> 4));
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (cb | t | k) != 0 ? 1u : 0u);
+              }
             }
-          } else {
+          } else if (p.ntaps == 9) {
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
               mbar_wait(&b_full[b], bp);
               tc_fence_after();
               const uint64_t da = da0 + (uint64_t)(((t / 3) * (HALO_TW + 2) + (t % 3)) * 8);
+              const uint64_t db = db_base + (uint64_t)(b * (Cfg::B_BYTES >> 4));
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (cb | t | k) != 0 ? 1u : 0u);
+              umma_commit(&b_empty[b]);
+              if (++b == BS) { b = 0; bp ^= 1; }
+            }
+          } else {
+            for (int t = 0; t < p.ntaps; ++t) {
+              mbar_wait(&b_full[b], bp);
+              tc_fence_after();
+              const int dy = t / p.tap_kw, dx = t - dy * p.tap_kw;
+              const uint64_t da = da0 + (uint64_t)(((dy + p.tap_oy) * (HALO_TW + 2) + dx + p.tap_ox) * 8);
               const uint64_t db = db_base + (uint64_t)(b * (Cfg::B_BYTES >> 4));
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (cb | t | k) != 0 ? 1u : 0u);
@@ -804,7 +833,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         aph ^= (na / AS) & 1;
         as = na % AS;
         if (!p.b_resident) {
-          const int nb = bs + 9 * p.cin_blocks;
+          const int nb = bs + p.ntaps * p.cin_blocks;
           bph ^= (nb / BS) & 1;
           bs = nb % BS;
         }
@@ -879,6 +908,220 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- halo conv on CTA pairs
+// The narrow halo convs are bound by shared-memory bandwidth, not by the tensor pipe: with N <= 128 every UMMA reads as
+// many operand bytes from smem as it has cycles to compute, and the streamed weight tiles are written there as well.
+// cta_group::2 halves the weight side: the two CTAs of a cluster take two neighbouring 128-pixel tiles (M = 256), each
+// loads and holds only HALF of every weight tile (N/2 rows), and the leader's single thread issues MMAs that read A
+// from both SMs and the two weight halves; each CTA's TMEM receives its own 128 x N accumulator and its epilogue runs
+// unchanged.  Both CTAs' TMA loads complete on the LEADER's full barriers; the leader's tcgen05.commit multicasts the
+// empty / accumulator-ready arrivals to both CTAs; the peer's epilogue releases the accumulator with remote arrives.
+template <int BN>
+struct Halo2Cfg {
+  static constexpr int B_BYTES = (BN / 2) * 128;                        // this CTA's half of one tap's weight tile
+  static constexpr int A_STAGES = 4;
+  static constexpr int B_STAGES = (BN == 64) ? 9 : 8;
+  static constexpr int STAGING_BYTES = NUM_SLOTS * PANEL_BYTES;
+  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : 256;
+  static constexpr int SMEM_BYTES = A_STAGES * HALO_A_STRIDE + B_STAGES * B_BYTES + STAGING_BYTES + 2 * BN * 4 + 1024 + 512;
+  static_assert(SMEM_BYTES <= 232448, "halo2 conv smem budget");
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
+                  const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
+  using Cfg = Halo2Cfg<BN>;
+  constexpr int AS = Cfg::A_STAGES, BS = Cfg::B_STAGES;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + AS * HALO_A_STRIDE;
+  uint8_t* staging = smem_b + BS * Cfg::B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
+  uint64_t* a_full = bars;                   // leader's are the live ones (both CTAs' loads land there)
+  uint64_t* a_empty = bars + AS;             // per CTA, fed by the leader's multicast commit
+  uint64_t* b_full = bars + 2 * AS;
+  uint64_t* b_empty = bars + 2 * AS + BS;
+  uint64_t* tmem_full = bars + 2 * AS + 2 * BS;        // per CTA (multicast commit)
+  uint64_t* tmem_empty = tmem_full + 2;                // leader's: 2 x 256 epilogue threads
+  uint64_t* res_bar = tmem_full + 4;
+  uint64_t* slot_ready = tmem_full + 8;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 12);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int num_tiles = p.m_tiles;                     // n_tiles == 1, m_tiles even (host checks)
+  const int cin_pad = p.cin_blocks * BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.fast_epi) tma_prefetch_desc(&tmO);
+    if (p.has_res_map) tma_prefetch_desc(&tmR);
+    if (p.fast_epi && p.epi_mode == PGT_EPI_SFT) tma_prefetch_desc(&tmX);
+    for (int i = 0; i < AS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * EPI_WARPS);            // one arrive per epilogue warp of either CTA
+      mbar_init(&res_bar[2 * i], 1);
+      mbar_init(&res_bar[2 * i + 1], 1);
+      mbar_init(&slot_ready[2 * i], EPI_WARPS * 32);
+      mbar_init(&slot_ready[2 * i + 1], EPI_WARPS * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta<Cfg::TMEM_COLS>(tmem_ptr);
+    tc_fence_before();
+  }
+  __syncthreads();
+  cluster_sync_all();                                  // the peer's barriers exist before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs; leader arms the barriers)
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    const uint32_t a_full0 = mapa_u32(smem_u32(a_full), 0), b_full0 = mapa_u32(smem_u32(b_full), 0);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int n0, y0, x0;
+      decode_conv_tile(p, tile, n0, y0, x0);
+      {
+        const int pt = tile + PREFETCH_TILES * (int)gridDim.x;
+        if (BN == 64 && pt < num_tiles && elect_one()) {
+          int pn0, py0, px0;
+          decode_conv_tile(p, pt, pn0, py0, px0);
+          for (int cb = 0; cb < p.cin_blocks; ++cb) tma_prefetch_4d(&tmA, cb * BK, px0 - 1, py0 - 1, pn0);
+          if (p.has_res_map) {
+            const int rw = p.out_dtype == PGT_BF16 ? 64 : 32;
+            for (int c = 0; c < BN && c < p.N; c += rw) {
+              tma_prefetch_4d(&tmR, c, px0, py0, pn0);
+              if (p.epi_mode == PGT_EPI_SFT) tma_prefetch_4d(&tmX, c, px0, py0, pn0);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      for (int cb = 0; cb < p.cin_blocks; ++cb) {
+        mbar_wait(&a_empty[as], aph ^ 1);
+        if (elect_one()) {
+          if (rank == 0) mbar_arrive_expect_tx(&a_full[as], 2 * HALO_A_BYTES);
+          tma_load_4d_2sm(smem_a + as * HALO_A_STRIDE, &tmA, a_full0 + as * 8, cb * BK, x0 - 1, y0 - 1, n0);
+        }
+        __syncwarp();
+        if (++as == AS) { as = 0; aph ^= 1; }
+        if (p.b_resident && tile != (int)blockIdx.x) continue;   // this CTA's weight halves stay resident in the ring
+        for (int t = 0; t < p.ntaps; ++t) {
+          mbar_wait(&b_empty[bs], bph ^ 1);
+          if (elect_one()) {
+            if (rank == 0) mbar_arrive_expect_tx(&b_full[bs], 2 * Cfg::B_BYTES);
+            tma_load_2d_2sm(smem_b + bs * Cfg::B_BYTES, &tmB, b_full0 + bs * 8, t * cin_pad + cb * BK, (int)rank * (BN / 2));
+          }
+          __syncwarp();
+          if (++bs == BS) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer: the pair leader's elected lane only
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        if (elect_one()) {
+          int a = as, b = bs;
+          uint32_t ap = aph, bp = bph;
+          const uint64_t da_base = umma_desc_k_sw128_sbo(smem_u32(smem_a), HALO_PITCH);
+          const uint64_t db_base = umma_desc_k_sw128(smem_u32(smem_b));
+          for (int cb = 0; cb < p.cin_blocks; ++cb) {
+            mbar_wait(&a_full[a], ap);
+            const uint64_t da0 = da_base + (uint64_t)(a * (HALO_A_STRIDE >> 4));
+            if (p.ntaps == 9) {
+#pragma unroll
+              for (int t = 0; t < 9; ++t) {
+                int slot = b;
+                if (p.b_resident) {
+                  slot = cb * 9 + t;
+                  if (it == 0) mbar_wait(&b_full[slot], 0);
+                } else {
+                  mbar_wait(&b_full[b], bp);
+                }
+                tc_fence_after();
+                const uint64_t da = da0 + (uint64_t)(((t / 3) * (HALO_TW + 2) + (t % 3)) * 8);
+                const uint64_t db = db_base + (uint64_t)(slot * (Cfg::B_BYTES >> 4));
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) umma_bf16_ss_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (cb | t | k) != 0 ? 1u : 0u);
+                if (!p.b_resident) {
+                  umma_commit_2cta(&b_empty[b]);
+                  if (++b == BS) { b = 0; bp ^= 1; }
+                }
+              }
+            } else {
+              for (int t = 0; t < p.ntaps; ++t) {
+                int slot = b;
+                if (p.b_resident) {
+                  slot = cb * p.ntaps + t;
+                  if (it == 0) mbar_wait(&b_full[slot], 0);
+                } else {
+                  mbar_wait(&b_full[b], bp);
+                }
+                tc_fence_after();
+                const int dy = t / p.tap_kw, dx = t - dy * p.tap_kw;
+                const uint64_t da = da0 + (uint64_t)(((dy + p.tap_oy) * (HALO_TW + 2) + dx + p.tap_ox) * 8);
+                const uint64_t db = db_base + (uint64_t)(slot * (Cfg::B_BYTES >> 4));
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) umma_bf16_ss_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (cb | t | k) != 0 ? 1u : 0u);
+                if (!p.b_resident) {
+                  umma_commit_2cta(&b_empty[b]);
+                  if (++b == BS) { b = 0; bp ^= 1; }
+                }
+              }
+            }
+            umma_commit_2cta(&a_empty[a]);
+            if (++a == AS) { a = 0; ap ^= 1; }
+          }
+          umma_commit_2cta(&tmem_full[acc]);
+        }
+        __syncwarp();
+        const int na = as + p.cin_blocks;
+        aph ^= (na / AS) & 1;
+        as = na % AS;
+        if (!p.b_resident) {
+          const int nb = bs + p.ntaps * p.cin_blocks;
+          bph ^= (nb / BS) & 1;
+          bs = nb % BS;
+        }
+      }
+    }
+  } else if (warp < 2 + EPI_WARPS) {
+    EpiCtx ctx{staging, tmem_full, tmem_empty, res_bar, slot_ready, tmem_base, mapa_u32(smem_u32(tmem_empty), 0)};
+    epilogue_loop<BN>(p, ctx, warp, lane, num_tiles);
+  } else {
+    EpiCtx ctx{staging, tmem_full, tmem_empty, res_bar, slot_ready, tmem_base, 0};
+    epilogue_dma_loop<BN>(p, ctx, tmO, tmR, tmX, lane, num_tiles);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                  // neither CTA retires while the peer may still signal it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -1027,7 +1270,7 @@ static int launch_halo(const CUtensorMap& tmA, const void* W, int ldw, GemmParam
   rc = setup_epilogue_maps(p, tmA, tmO, tmR, tmX);
   if (rc != PGT_OK) return rc;
   p.n_tiles = ceil_div(p.N, BN);
-  p.b_resident = (9 * p.cin_blocks == Cfg::B_STAGES && p.n_tiles == 1) ? 1 : 0;
+  p.b_resident = (p.ntaps * p.cin_blocks <= Cfg::B_STAGES && p.n_tiles == 1) ? 1 : 0;
   static bool attr_set = false;
   if (!attr_set) {
     PGT_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<BN, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -1043,6 +1286,35 @@ static int launch_halo(const CUtensorMap& tmA, const void* W, int ldw, GemmParam
     ProfScope ps(PGT_PROF_GEMM, p.flops, stream, desc);
     conv_halo_kernel<BN, GN><<<grid, GN ? GEMM_THREADS + HALO_GN_THREADS : GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(
         tmA, tmB, tmO, tmR, tmX, p);
+  }
+  PGT_LAUNCH_OK();
+  return PGT_OK;
+}
+
+template <int BN>
+static int launch_halo2(const CUtensorMap& tmA, const void* W, int ldw, GemmParams& p, cudaStream_t stream) {
+  using Cfg = Halo2Cfg<BN>;
+  CUtensorMap tmB, tmO, tmR, tmX;
+  int rc = encode_weight_map(&tmB, W, ldw, p.K, p.N, BN / 2);            // each CTA loads half of the N rows
+  if (rc != PGT_OK) return rc;
+  rc = setup_epilogue_maps(p, tmA, tmO, tmR, tmX);
+  if (rc != PGT_OK) return rc;
+  p.n_tiles = 1;
+  p.b_resident = (p.ntaps * p.cin_blocks <= Cfg::B_STAGES) ? 1 : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PGT_CUDA_OK(cudaFuncSetAttribute(conv_halo2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
+  grid &= ~1;                                                            // whole CTA pairs
+  {
+    char desc[96];
+    if (prof_enabled())
+      snprintf(desc, sizeof(desc), "halo%d x2cta F%d H%d W%d K%d N%d BN%d e%d r%d", p.tap_kw, p.F, p.H, p.W, p.K, p.N, BN,
+               p.fast_epi, p.b_resident);
+    ProfScope ps(PGT_PROF_GEMM, p.flops, stream, desc);
+    conv_halo2_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, tmR, tmX, p);
   }
   PGT_LAUNCH_OK();
   return PGT_OK;
@@ -1159,8 +1431,11 @@ static int conv_impl(const void* x, int F, int Hin, int Win, int Cin, int ldx, c
   }
   // 128-pixel tile = tn frames x th rows x tw columns
   static const bool no_halo = getenv("PGT_NO_HALO") != nullptr;
-  const bool halo = !no_halo && up_phase < 0 && stride == 1 && ksize == 3 && pad_y == 1 && pad_x == 1 && Cout <= 128 && Hin >= HALO_TH &&
-                    Win >= HALO_TW;
+  const bool halo = !no_halo && stride == 1 && Cout <= 128 && Hin >= HALO_TH && Win >= HALO_TW &&
+                    ((up_phase < 0 && ksize == 3 && pad_y == 1 && pad_x == 1) || (up_phase >= 0 && ksize == 2));
+  p.ntaps = ksize * ksize; p.tap_kw = ksize;
+  p.tap_oy = up_phase >= 0 ? (up_phase >> 1) : 0;          // phase (py, px): tap (dy, dx) reads slab row dy + py, col dx + px
+  p.tap_ox = up_phase >= 0 ? (up_phase & 1) : 0;
   int tw = 1, th = 1, tn;
   if (halo) {
     tw = HALO_TW; th = HALO_TH;
@@ -1195,6 +1470,13 @@ static int conv_impl(const void* x, int F, int Hin, int Win, int Cin, int ldx, c
         p.gn_c = Cin;
         return Cout <= 64 ? launch_halo<64, true>(tmA, Wp, ldw, p, st) : launch_halo<128, true>(tmA, Wp, ldw, p, st);
       }
+      static const bool no_pair = getenv("PGT_NO_2CTA") != nullptr;
+      // CTA pairs (whole pairs of tiles only).  Measured at 16 clips of 512^2: 128-wide 3x3 layers gain 5-8 % (their
+      // streamed weight tiles stop competing with the A views for smem bandwidth); 64-wide layers are bound by the A
+      // operand reads, which pairing does not reduce, and lose to the pair's lock-step — they stay on single CTAs.
+      static const bool pair64 = getenv("PGT_2CTA_N64") != nullptr;
+      if (!no_pair && (p.m_tiles % 2) == 0 && p.m_tiles >= 2 && p.out_layout == PGT_OUT_NHWC && (pair64 || (Cout > 64 && up_phase < 0)))
+        return Cout <= 64 ? launch_halo2<64>(tmA, Wp, ldw, p, st) : launch_halo2<128>(tmA, Wp, ldw, p, st);
       return Cout <= 64 ? launch_halo<64, false>(tmA, Wp, ldw, p, st) : launch_halo<128, false>(tmA, Wp, ldw, p, st);
     }
   } else {
@@ -1219,7 +1501,8 @@ static int conv_impl(const void* x, int F, int Hin, int Win, int Cin, int ldx, c
 extern "C" int pgt_conv_tiles_per_frame(int Hin, int Win, int Cout, int ksize, int stride, int pad_lo) {
   static const bool no_halo = getenv("PGT_NO_HALO") != nullptr;
   const int H = Hin / stride, W = Win / stride;
-  const bool halo = !no_halo && stride == 1 && ksize == 3 && pad_lo == 1 && Cout <= 128 && Hin >= HALO_TH && Win >= HALO_TW;
+  const bool halo = !no_halo && stride == 1 && ((ksize == 3 && pad_lo == 1) || ksize == 2) && Cout <= 128 && Hin >= HALO_TH &&
+                    Win >= HALO_TW;      // ksize 2: an upsample phase (pgt_conv_up2x_bf16)
   int tw = 1, th = 1;
   if (halo) { tw = HALO_TW; th = HALO_TH; }
   else {

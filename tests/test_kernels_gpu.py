@@ -191,7 +191,8 @@ def test_conv1x1_stride2():
     check_close(out, conv_ref(x, w, None, stride=2, pad=(0, 0, 0, 0)), 'conv1x1 s2')
 
 
-@pytest.mark.parametrize('Fr,H,W,C', [(3, 8, 8, 64), (3, 16, 16, 128), (2, 4, 4, 512), (3, 32, 32, 256)])
+@pytest.mark.parametrize('Fr,H,W,C', [(3, 8, 8, 64), (3, 16, 16, 128), (2, 4, 4, 512), (3, 32, 32, 256), (2, 40, 20, 64),
+                                      (2, 32, 24, 96)])
 def test_conv_up2x_folded(Fr, H, W, C):
     """nearest x2 + conv3x3 (tdcrqvae3_arch.py:45-52) as four 2x2 phase convs on the source resolution."""
     from pgtformer_b200.engine import _pack_up2x
