@@ -230,31 +230,36 @@ layernorm_kernel(const void* __restrict__ xin, int ldx, int x_dtype, int T, cons
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c0 = (i * 32 + lane) * 8;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { g[i][j] = __ldg(gamma + c0 + j); bt[i][j] = __ldg(beta + c0 + j); }
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+    g[i][0] = g0.x; g[i][1] = g0.y; g[i][2] = g0.z; g[i][3] = g0.w; g[i][4] = g1.x; g[i][5] = g1.y; g[i][6] = g1.z; g[i][7] = g1.w;
+    bt[i][0] = b0.x; bt[i][1] = b0.y; bt[i][2] = b0.z; bt[i][3] = b0.w; bt[i][4] = b1.x; bt[i][5] = b1.y; bt[i][6] = b1.z; bt[i][7] = b1.w;
   }
+  // the kernel is issue-bound before it is HBM-bound (10 instructions per element with two-pass statistics):
+  // one pass (sum, sum of squares) and the normalisation as two FMAs per element
 #pragma unroll
   for (int r = 0; r < LN_ROWS; ++r) {
     const int row = row0 + r;
-    float s = 0.f;
+    float s = 0.f, q = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += v[r][i][j];
-    const float mean = warp_sum(s) * (1.0f / C);
-    float q = 0.f;
+      for (int j = 0; j < 8; ++j) { s += v[r][i][j]; q = fmaf(v[r][i][j], v[r][i][j], q); }
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = v[r][i][j] - mean; q += d * d; }
-    const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    const float mean = s * (1.0f / C);
+    const float rstd = rsqrtf(fmaxf(q * (1.0f / C) - mean * mean, 0.f) + eps);
+    const float nm = -mean * rstd;
     if (row < T) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int c0 = (i * 32 + lane) * 8;
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (v[r][i][j] - mean) * rstd * g[i][j] + bt[i][j];
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(fmaf(v[r][i][j], rstd, nm), g[i][j], bt[i][j]);
         store8_bf16(y + (size_t)row * ldy + c0, o);
         if (y2 != nullptr) {
           float pv[8];
