@@ -171,6 +171,13 @@ int pgt_groupnorm_silu(const void* x, int ldx, int F, int HW, int C, const float
 int pgt_layernorm(const void* x, int ldx, int x_dtype, int T, int C, const float* gamma, const float* beta,
                   float eps, void* y, int ldy, const void* pos, int ldpos, void* y2, int ldy2, void* stream);
 
+/* ---- LayerNorm fused into the GEMM that consumes it (C = 256, N % 256 == 0):  out[T, N] = LN(x) W^T + bias in ONE kernel —
+ * the normalised token matrix never reaches HBM.  W: bf16 [N, ldw] row-major ([out, in]).  Returns PGT_ERR_UNSUPPORTED
+ * otherwise.  Replaces norm1 + the q / kv projections of VSTSREncoderTransformerBlock / WindowAttention3D
+ * (modules/rstt_layers.py:116-132,176-188,326-330). */
+int pgt_ln_linear_bf16(const void* x, int ldx, int T, int C, const float* ln_g, const float* ln_b, float eps,
+                       const void* W, int ldw, int N, const float* bias, void* out, int ldo, void* stream);
+
 /* ---- fused Swin MLP half-block (C = 256):  out = x + fc2(GELU(fc1(LayerNorm(x)))) in ONE kernel — the hidden tile
  * stays in shared memory / TMEM, x is read once and out written once.  W1, W2: bf16 [C, C] row-major ([out, in]);
  * gn_stats: optional GroupNorm partials of `out` as in pgt_epilogue.  Returns PGT_ERR_UNSUPPORTED for C != 256.

@@ -54,6 +54,8 @@ SIGNATURES = {
                                    c_void_p, c_int, c_void_p, c_void_p]),
     'pgt_layernorm': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int,
                               c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    'pgt_ln_linear_bf16': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int,
+                                   c_void_p, c_void_p, c_int, c_void_p]),
     'pgt_swin_mlp_bf16': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     'pgt_window_attention': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

@@ -119,6 +119,7 @@ class Engine:
     def _new(self, *shape, dtype=BF):
         return torch.empty(*shape, dtype=dtype, device=self.dev)
 
+    fuse_ln_qkv = True        # norm1 + q/kv projection of the C=256 Swin blocks as one kernel
     fuse_swin_mlp = True      # LN + fc1 + GELU + fc2 + residual of the C=256 Swin blocks as one kernel
     # GroupNorm+SiLU applied inside the consuming 3x3 conv (pgt_conv_gn_bf16, bit-identical).  Off by default: the
     # narrow (Cout <= 128) halo convs are bound by shared-memory operand reads, so the in-place slab transform costs
@@ -186,8 +187,13 @@ class Engine:
         """VSTSREncoderTransformerBlock (`modules/rstt_layers.py:284-338`) on [F,H,W,C]."""
         Fr, H, W, C = x.shape
         w = self.w
-        y = ops.layernorm(x, w[p + '.norm1.weight'], w[p + '.norm1.bias'], self._new(Fr, H, W, C))
-        qkv = self._lin(y, p + '.attn.qkv', 3 * C)
+        if C == 256 and self.fuse_ln_qkv:
+            # norm1 + the fused q/kv projection in one kernel (LN applied to the tile in shared memory)
+            qkv = ops.ln_linear(x, w[p + '.norm1.weight'], w[p + '.norm1.bias'], w[p + '.attn.qkv.weight'],
+                                w[p + '.attn.qkv.bias'], self._new(Fr, H, W, 3 * C))
+        else:
+            y = ops.layernorm(x, w[p + '.norm1.weight'], w[p + '.norm1.bias'], self._new(Fr, H, W, C))
+            qkv = self._lin(y, p + '.attn.qkv', 3 * C)
         a = ops.window_attention(qkv, Fr // 3, H, W, C, heads, shift, w[p + '.attn.bias_tab'], self._new(Fr, H, W, C))
         x = self._lin(a, p + '.attn.proj', C, residual=x)
         if C == 256 and self.fuse_swin_mlp:

@@ -219,6 +219,16 @@ def layernorm(x, gamma, beta, out, eps=1e-5, pos=None, out2=None):
     return out
 
 
+def ln_linear(x, ln_g, ln_b, w, bias, out, eps=1e-5):
+    """out = LN(x) @ w^T + bias fused (C == 256, N % 256 == 0); x [..., 256] bf16, w [N, 256] bf16."""
+    lib = L.load()
+    T, C, ldx = _rows(x)
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.stride(1) == 1 and out.dtype == torch.bfloat16
+    L.check(lib.pgt_ln_linear_bf16(_p(x), ldx, T, C, _p(ln_g), _p(ln_b), eps, _p(w), w.stride(0), w.shape[0], _p(bias),
+                                   _p(out), _rows(out)[2], _stream()))
+    return out
+
+
 def swin_mlp(x, ln_g, ln_b, w1, b1, w2, b2, out, eps=1e-5, gn_stats=None):
     """out = x + fc2(gelu(fc1(LN(x)))) fused (C == 256); x, out: [..., C] bf16 with a uniform row stride."""
     lib = L.load()

@@ -579,3 +579,18 @@ def test_conv_with_fused_input_groupnorm(Fr, H, W, Cin, Cout, res, nchw, fused_s
         o.groupnorm_apply_stats(got, g2, b2, y, stats, tpf * 4)
         gref = F.silu(F.group_norm(got.float().cpu().permute(0, 3, 1, 2), 32, g2.cpu(), b2.cpu(), eps=1e-6)).permute(0, 2, 3, 1)
         check_close(y, gref, 'stats after fused-GN conv', bf16_out=True, rel=3e-3)
+
+
+@pytest.mark.parametrize('T,N', [(128, 768), (1000, 768), (12288, 256), (5000, 512)])
+def test_ln_linear_fused(T, N):
+    """out = LN(x) W^T + b in one kernel vs the fp32 composition on bf16-rounded operands."""
+    o = ops()
+    C = 256
+    x = bf(rnd((T, C), 200) * 1.5 + 0.1)
+    g, b = 1 + 0.1 * rnd((C,), 201), 0.1 * rnd((C,), 202)
+    w, wb = bf(rnd((N, C), 203, C ** -0.5)), rnd((N,), 204, 0.1)
+    out = torch.full((T, N), 9.0, dtype=torch.bfloat16, device=DEV)
+    o.ln_linear(x.to(DEV), g.to(DEV), b.to(DEV), w.to(DEV), wb.to(DEV), out)
+    torch.cuda.synchronize()
+    y = bf(F.layer_norm(x.float(), (C,), g, b, 1e-5)).float()
+    check_close(out, y @ w.float().t() + wb, 'fused LN + linear', bf16_out=True, rel=3e-3)

@@ -1,0 +1,25 @@
+#!/bin/bash
+# Runs on the GPU box (under gpurun): collects the evidence summarised under profiles/ into gpurun_out/prof/.
+#   launches.csv   ncu launch list (gpu__time_duration) of bench.py --steps 1 --warmup 3
+#   layers.txt     per-launch CUDA-event times of one forward, grouped by shape
+#   ops_<name>.csv ncu --set full raw page of representative heavy shapes run in isolation (tools/ncu_ops.py)
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out/prof
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/prof/launches.csv \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/prof/launches_bench.log 2>&1
+gzip -f gpurun_out/prof/launches.csv
+timeout 300 python tools/layer_profile.py 16 512 > gpurun_out/prof/layers.txt 2>&1
+for op in halo64 halo128 conv256 linear256 swin_mlp rgb gn; do
+  case $op in
+    halo64|halo128) rx='regex:conv_halo' ;;
+    conv256|linear256) rx='regex:gemm_tc_kernel' ;;
+    swin_mlp) rx='regex:swin_mlp' ;;
+    rgb) rx='regex:rgb_conv' ;;
+    gn) rx='regex:gn_apply' ;;
+  esac
+  timeout 200 ncu --set full --clock-control none -k "$rx" -s 2 -c 1 -o gpurun_out/prof/ops_$op -f python tools/ncu_ops.py $op > gpurun_out/prof/ops_$op.log 2>&1
+  ncu -i gpurun_out/prof/ops_$op.ncu-rep --page raw --csv > gpurun_out/prof/ops_$op.csv 2>/dev/null
+  rm -f gpurun_out/prof/ops_$op.ncu-rep
+done
+ls -la gpurun_out/prof

@@ -20,13 +20,15 @@ if which in ('halo64', 'halo128', 'conv256'):
     out = torch.empty(F, H, H, N, device=dev, dtype=torch.bfloat16)
     for _ in range(3):
         ops.conv(x, w, N, out, bias=b, residual=res)
-elif which == 'conv_in':
+elif which == 'rgb':
+    from pgtformer_b200.engine import _pack_rgb
     x = torch.rand(F, 3, 512, 512, device=dev)
-    w = torch.randn(64, 3, 3, 3, device=dev) * 0.1
+    w = _pack_rgb(torch.randn(64, 3, 3, 3, device=dev) * 0.1)
     b = torch.zeros(64, device=dev)
     out = torch.empty(F, 512, 512, 64, device=dev, dtype=torch.bfloat16)
+    stats = torch.zeros(F * 2048 * 4 * 64, device=dev)
     for _ in range(3):
-        ops.conv_in_rgb(x, w, b, out)
+        ops.conv_rgb(x, w, b, out, 3, 1, 1, gn_stats=stats)
 elif which == 'gn':
     x = torch.randn(F, 512, 512, 64, device=dev).bfloat16()
     g, b = torch.ones(64, device=dev), torch.zeros(64, device=dev)
