@@ -51,9 +51,9 @@ ln_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* y_ready = bars + 2;      // compute (256) -> MMA
   uint64_t* acc_full = bars + 3;     // [2] MMA commit -> compute
   uint64_t* acc_free = bars + 5;     // [2] compute (256) -> MMA
-  uint64_t* so_free = bars + 7;      // DMA (store has read the staging tile) -> compute
-  uint64_t* out_ready = bars + 8;    // compute (256) -> DMA
-  uint64_t* w_full = bars + 9;       // [LL_WST]
+  uint64_t* so_free = bars + 7;      // [2] DMA (store has read staging half h) -> compute
+  uint64_t* out_ready = bars + 9;    // [2] compute (256) -> DMA
+  uint64_t* w_full = bars + 11;      // [LL_WST]
   uint64_t* w_empty = w_full + LL_WST;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_empty + LL_WST);
 
@@ -62,7 +62,7 @@ ln_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmO); tma_prefetch_desc(&tmW);
     mbar_init(x_full, 1); mbar_init(sx_free, 1); mbar_init(y_ready, 256);
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], 256); }
-    mbar_init(so_free, 1); mbar_init(out_ready, 256);
+    for (int i = 0; i < 2; ++i) { mbar_init(&so_free[i], 1); mbar_init(&out_ready[i], 256); }
     for (int i = 0; i < LL_WST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     fence_barrier_init();
   }
@@ -134,7 +134,6 @@ ln_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;                    // which 128-column half of the row this thread owns
     const int r = quad * 32 + lane;
-    const int c_lo = half * 128;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
       // ---- LayerNorm(x) in place (two threads per row; the halves meet through smem)
@@ -199,37 +198,44 @@ ln_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + (g & 1) * LL_C;
         mbar_wait(&acc_full[g & 1], (g >> 1) & 1);
         tc_fence_after();
-        mbar_wait(so_free, (g & 1) ^ 1);             // the previous block's store has read the staging tile
+        // the [128 x 256] block leaves in two 128-column halves through a ping-pong pair of 32 KB staging buffers:
+        // the TMA store of one half reads its buffer while the warps fill the other
 #pragma unroll 1
-        for (int c0 = c_lo; c0 < c_lo + 128; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(t_row + c0, v);
-          tmem_ld_wait();
-          if (c0 == c_lo + 96) {                     // last TMEM read of this thread: the accumulator may be reused
-            tc_fence_before();
-            mbar_arrive(&acc_free[g & 1]);
-          }
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + j * LL_C + c0);
-          uint8_t* dst = sO + (c0 >> 6) * LL_SUB + r * 128;
-          const int ch0 = (c0 & 63) >> 3;
+        for (int hp = 0; hp < 2; ++hp) {
+          mbar_wait(&so_free[hp], (g & 1) ^ 1);         // the store that last used this half has read it
+#pragma unroll 1
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c0 = hp * 128 + half * 64 + cc * 32;
+            uint32_t v[32];
+            tmem_ld_32x32(t_row + c0, v);
+            tmem_ld_wait();
+            if (hp == 1 && cc == 1) {                    // last TMEM read of this thread: the accumulator may be reused
+              tc_fence_before();
+              mbar_arrive(&acc_free[g & 1]);
+            }
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + j * LL_C + c0);
+            uint8_t* dst = sO + (c0 >> 6) * LL_SUB + r * 128;
+            const int ch0 = (c0 & 63) >> 3;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 ba = __ldg(b4 + 2 * i), bb = __ldg(b4 + 2 * i + 1);
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) + ba.x, __uint_as_float(v[8 * i + 1]) + ba.y);
-            o.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) + ba.z, __uint_as_float(v[8 * i + 3]) + ba.w);
-            o.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) + bb.x, __uint_as_float(v[8 * i + 5]) + bb.y);
-            o.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) + bb.z, __uint_as_float(v[8 * i + 7]) + bb.w);
-            *reinterpret_cast<uint4*>(dst + (((ch0 + i) ^ (r & 7)) << 4)) = o;
+            for (int i = 0; i < 4; ++i) {
+              const float4 ba = __ldg(b4 + 2 * i), bb = __ldg(b4 + 2 * i + 1);
+              uint4 o;
+              o.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) + ba.x, __uint_as_float(v[8 * i + 1]) + ba.y);
+              o.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) + ba.z, __uint_as_float(v[8 * i + 3]) + ba.w);
+              o.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) + bb.x, __uint_as_float(v[8 * i + 5]) + bb.y);
+              o.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) + bb.z, __uint_as_float(v[8 * i + 7]) + bb.w);
+              *reinterpret_cast<uint4*>(dst + (((ch0 + i) ^ (r & 7)) << 4)) = o;
+            }
           }
+          fence_proxy_async();
+          mbar_arrive(&out_ready[hp]);
         }
-        fence_proxy_async();
-        mbar_arrive(out_ready);
       }
     }
   } else {
     // ------------------------------------------------------------------ DMA warp
     int it = 0;
+    int pending = -1;                                  // staging half of the newest committed store (not yet released)
     if (lane == 0 && (int)blockIdx.x < p.m_tiles) {
       mbar_arrive_expect_tx(x_full, 4 * LL_SUB);
       for (int kb = 0; kb < 4; ++kb) tma_load_2d(sX + kb * LL_SUB, &tmX, x_full, kb * 64, blockIdx.x * LL_BM);
@@ -250,14 +256,20 @@ ln_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             __syncwarp();
           }
         }
-        mbar_wait(out_ready, g & 1);
-        if (lane == 0) {
-          for (int kb = 0; kb < 4; ++kb) tma_store_2d(&tmO, sO + kb * LL_SUB, j * LL_C + kb * 64, tile * LL_BM);
-          bulk_commit();
-          bulk_wait_read<0>();
-          mbar_arrive(so_free);
+        for (int hp = 0; hp < 2; ++hp) {
+          mbar_wait(&out_ready[hp], g & 1);
+          if (lane == 0) {
+            for (int q = 0; q < 2; ++q)
+              tma_store_2d(&tmO, sO + (2 * hp + q) * LL_SUB, j * LL_C + hp * 128 + q * 64, tile * LL_BM);
+            bulk_commit();
+            if (pending >= 0) {
+              bulk_wait_read<1>();                       // the store before this one has read its half
+              mbar_arrive(&so_free[pending]);
+            }
+          }
+          pending = hp;
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
     if (lane == 0) bulk_wait0();
