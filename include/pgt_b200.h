@@ -255,6 +255,18 @@ int pgt_nchw_f32_to_nhwc_bf16(const float* x, int F, int C, int HW, const float*
                               int ldy, void* stream);
 int pgt_nhwc_bf16_to_f32(const void* x, int ldx, int F, int HW, int C, float* y, int to_nchw, void* stream);
 
+/* ---- streaming video front / back end: the two conversions of the reference's frame loop and the
+ * frame gather that lets per-frame work be computed once per distinct frame.
+ *   pgt_u8hwc_to_f32nchw: rgb24 [F, H, W, 3] -> fp32 [F, 3, H, W], y = (float)(v / 255.0) exactly as numpy forms it
+ *     (rgbnp2tensor, inference.py:6-10).
+ *   pgt_f32nchw_to_u8hwc: frames first, first+step, ... (n of them) of fp32 [*, 3, H, W] -> rgb24 [n, H, W, 3] with
+ *     uint8(clamp(x, 0, 1) * 255) (apply_net_to_frames, inference.py:15-19); first = 1, step = 3 selects the middle
+ *     frame of every clip.
+ *   pgt_gather_frames: y[f] = x[idx[f]] for frames of frame_bytes bytes (multiple of 16); idx: DEVICE int32 [n]. */
+int pgt_u8hwc_to_f32nchw(const void* x_u8, int F, int H, int W, float* y, void* stream);
+int pgt_f32nchw_to_u8hwc(const float* x, int first, int step, int n, int H, int W, void* y_u8, void* stream);
+int pgt_gather_frames(const void* x, long long frame_bytes, const int* idx_dev, int n, void* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

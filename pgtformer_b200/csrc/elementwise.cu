@@ -271,3 +271,86 @@ extern "C" int pgt_regroup_frames(const void* x, int ldx, int clips, int P, int 
   PGT_LAUNCH_OK();
   return PGT_OK;
 }
+
+
+// ---------------------------------------------------------------- streaming video front / back end
+// The reference's loop (inference.py:6-19,37-76) turns rgb24 frames into float tensors with numpy
+// (`np.array(rgb / 255.0, np.float32)`: a double division rounded to fp32), runs the model on the window
+// (f[i-1], f[i], f[i+1]) and writes `clamp(out[0][1], 0, 1) * 255` truncated to uint8.  These kernels are those two
+// conversions, and the frame gather that lets per-frame work (BiSeNet, the attention-free encoder levels) be computed
+// once per distinct frame and handed to every window that contains the frame.
+namespace pgt {
+__constant__ float c_u8_to_unit[256];             // (float)(v / 255.0) evaluated in double on the host
+
+__global__ void u8hwc_to_f32nchw_kernel(const uint8_t* __restrict__ x, size_t HW, size_t total, float* __restrict__ y) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t f = i / HW, p = i - f * HW;
+    const uint8_t* s = x + (f * HW + p) * 3;
+    float* d = y + f * 3 * HW + p;
+    d[0] = c_u8_to_unit[s[0]];
+    d[HW] = c_u8_to_unit[s[1]];
+    d[2 * HW] = c_u8_to_unit[s[2]];
+  }
+}
+
+__global__ void f32nchw_to_u8hwc_kernel(const float* __restrict__ x, size_t HW, int first, int step, size_t total,
+                                        uint8_t* __restrict__ y) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t j = i / HW, p = i - j * HW;
+    const float* s = x + ((size_t)first + j * step) * 3 * HW + p;
+    uint8_t* d = y + (j * HW + p) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = fminf(fmaxf(s[c * HW], 0.f), 1.f) * 255.0f;     // torch.clamp, then the fp32 product numpy forms
+      d[c] = (uint8_t)v;                                             // astype(uint8) of a value in [0, 255]: truncation
+    }
+  }
+}
+
+__global__ void gather_frames_kernel(const uint4* __restrict__ x, size_t vec_per_frame, const int* __restrict__ idx,
+                                     uint4* __restrict__ y) {
+  const uint4* s = x + (size_t)idx[blockIdx.y] * vec_per_frame;
+  uint4* d = y + (size_t)blockIdx.y * vec_per_frame;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < vec_per_frame; i += (size_t)gridDim.x * blockDim.x)
+    d[i] = __ldg(s + i);
+}
+}  // namespace pgt
+
+extern "C" int pgt_u8hwc_to_f32nchw(const void* x_u8, int F, int H, int W, float* y, void* stream) {
+  PGT_CHECK_ARG(x_u8 && y && F > 0 && H > 0 && W > 0);
+  static bool table = false;
+  if (!table) {
+    float t[256];
+    for (int v = 0; v < 256; ++v) t[v] = (float)((double)v / 255.0);
+    PGT_CUDA_OK(cudaMemcpyToSymbol(pgt::c_u8_to_unit, t, sizeof(t)));
+    table = true;
+  }
+  const size_t HW = (size_t)H * W, total = (size_t)F * HW;
+  ProfScope ps(PGT_PROF_MOVE, 15.0 * (double)total, static_cast<cudaStream_t>(stream), "pgt_u8hwc_to_f32nchw");
+  pgt::u8hwc_to_f32nchw_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint8_t*>(x_u8), HW, total, y);
+  PGT_LAUNCH_OK();
+  return PGT_OK;
+}
+
+extern "C" int pgt_f32nchw_to_u8hwc(const float* x, int first, int step, int n, int H, int W, void* y_u8, void* stream) {
+  PGT_CHECK_ARG(x && y_u8 && n > 0 && H > 0 && W > 0 && first >= 0 && step >= 1);
+  const size_t HW = (size_t)H * W, total = (size_t)n * HW;
+  ProfScope ps(PGT_PROF_MOVE, 15.0 * (double)total, static_cast<cudaStream_t>(stream), "pgt_f32nchw_to_u8hwc");
+  pgt::f32nchw_to_u8hwc_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, HW, first, step, total, static_cast<uint8_t*>(y_u8));
+  PGT_LAUNCH_OK();
+  return PGT_OK;
+}
+
+extern "C" int pgt_gather_frames(const void* x, long long frame_bytes, const int* idx_dev, int n, void* y, void* stream) {
+  PGT_CHECK_ARG(x && y && idx_dev && n > 0 && frame_bytes > 0 && frame_bytes % 16 == 0);
+  PGT_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  const size_t vec = (size_t)frame_bytes / 16;
+  ProfScope ps(PGT_PROF_MOVE, 2.0 * (double)n * frame_bytes, static_cast<cudaStream_t>(stream), "pgt_gather_frames");
+  unsigned bx = (unsigned)std::min<size_t>((vec + 255) / 256, 1024);
+  pgt::gather_frames_kernel<<<dim3(bx, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), vec, idx_dev, static_cast<uint4*>(y));
+  PGT_LAUNCH_OK();
+  return PGT_OK;
+}

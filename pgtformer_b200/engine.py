@@ -351,8 +351,10 @@ class Engine:
         return ops.assemble_cond(o0, o1, o2, self._new(Fr, H // 16, W // 16, 64))
 
     # ------------------------------------------------------------------ encoder / decoder
-    def encoder(self, x):
-        """Encoder.forward (`archs/tdcrqvae3_arch.py:540-573`); x fp32 NCHW -> (h [F,h,w,z], feats)."""
+    def encoder_frames(self, x):
+        """The per-frame prefix of Encoder.forward (`archs/tdcrqvae3_arch.py:540-560`): conv_in and every level before
+        the first one with attention, including the Downsample into it — nothing here looks across frames, so the
+        streaming pipeline runs it once per distinct frame.  Returns (h, feats, next level)."""
         a = self.arch
         Fr, _, H, W = x.shape
         # Cin = 3: the kernel builds the patch rows itself; its epilogue also yields block 0's GroupNorm statistics
@@ -364,25 +366,54 @@ class Engine:
             h._pgt_gn = (stats, tpf * 4)
         ops.conv_rgb(x, self.w['encoder.conv_in.weight'], self.w['encoder.conv_in.bias'], h, 3, 1, 1, gn_stats=stats)
         feats = []
-        for lvl in range(a.num_levels):
-            last = lvl == a.num_levels - 1
-            for blk in range(a.num_res_blocks):
-                # the next consumer of this level's output is a Normalize() only at the last level (mid.block_1);
-                # otherwise it is the stride-2 Downsample conv, whose own epilogue feeds the next level's norm1
-                nxt = last and blk == a.num_res_blocks - 1
-                h = self.td_resblock(h, 'encoder.down.%d.block.%d' % (lvl, blk), a.level_ch[lvl],
-                                     gn_next=nxt and not a.level_has_attn[lvl])
-                if a.level_has_attn[lvl]:
-                    h = self.encoder_layer(h, 'encoder.down.%d.attn.%d' % (lvl, blk), a.num_heads[lvl], a.depths[lvl],
-                                           gn_next=nxt)
-            feats.append(h)
-            if not last:
-                h = self._conv3(h, 'encoder.down.%d.downsample.conv' % lvl, a.level_ch[lvl], stride=2, pad_lo=0, gn_out=True)
+        lvl = 0
+        while lvl < a.num_levels - 1 and not a.level_has_attn[lvl]:
+            h = self._encoder_level(h, lvl, feats)
+            lvl += 1
+        return h, feats, lvl
+
+    def _encoder_level(self, h, lvl, feats):
+        a = self.arch
+        last = lvl == a.num_levels - 1
+        for blk in range(a.num_res_blocks):
+            # the next consumer of this level's output is a Normalize() only at the last level (mid.block_1);
+            # otherwise it is the stride-2 Downsample conv, whose own epilogue feeds the next level's norm1
+            nxt = last and blk == a.num_res_blocks - 1
+            h = self.td_resblock(h, 'encoder.down.%d.block.%d' % (lvl, blk), a.level_ch[lvl],
+                                 gn_next=nxt and not a.level_has_attn[lvl])
+            if a.level_has_attn[lvl]:
+                h = self.encoder_layer(h, 'encoder.down.%d.attn.%d' % (lvl, blk), a.num_heads[lvl], a.depths[lvl],
+                                       gn_next=nxt)
+        feats.append(h)
+        if not last:
+            h = self._conv3(h, 'encoder.down.%d.downsample.conv' % lvl, a.level_ch[lvl], stride=2, pad_lo=0, gn_out=True)
+        return h
+
+    def encoder_clips(self, h, feats, lvl):
+        """The rest of Encoder.forward (`:560-573`) on clip-major frames."""
+        a = self.arch
+        while lvl < a.num_levels:
+            h = self._encoder_level(h, lvl, feats)
+            lvl += 1
         h = self.td_resblock(h, 'encoder.mid.block_1', a.level_ch[-1])
         h = self.encoder_layer(h, 'encoder.mid.attn_1', a.num_heads[-1], a.depths[-1], gn_next=True)
         h = self.td_resblock(h, 'encoder.mid.block_2', a.level_ch[-1], gn_next=True)
         zc = 2 * a.z_channels if a.double_z else a.z_channels
         return self._conv3(h, 'encoder.conv_out', zc, gn='encoder.norm_out'), feats
+
+    def encoder(self, x):
+        """Encoder.forward (`archs/tdcrqvae3_arch.py:540-573`); x fp32 NCHW -> (h [F,h,w,z], feats)."""
+        h, feats, lvl = self.encoder_frames(x)
+        return self.encoder_clips(h, feats, lvl)
+
+    def _gather(self, t, idx):
+        """t[idx] along the frame dimension, GroupNorm statistics included."""
+        out = ops.gather_frames(t, idx, self._new(idx.numel(), *t.shape[1:], dtype=t.dtype))
+        gn = getattr(t, '_pgt_gn', None)
+        if gn is not None:
+            st = gn[0].view(t.shape[0], -1)
+            out._pgt_gn = (ops.gather_frames(st, idx, self._new(idx.numel(), st.shape[1], dtype=st.dtype)).view(-1), gn[1])
+        return out
 
     def decoder(self, z, feats=None, wgt=0.0):
         """Decoder.forward (`archs/tdcrqvae3_arch.py:672-707`) / the inlined variant with SFT fusion
@@ -452,12 +483,18 @@ class Engine:
 
     # ------------------------------------------------------------------ full forwards
     @torch.no_grad()
-    def forward(self, x, w=1.0, adain=True, code_only=False, force_codes=None):
+    def forward(self, x, w=1.0, adain=True, code_only=False, force_codes=None, frame_index=None):
         """PGTFormer.forward (`archs/pgtformer_arch.py:598-714`).  x: fp32 [b*3,3,H,W] in [0,1] on the
-        device.  Returns (out, logits [b*3,h,w,1,K], lq_feat [b*3,h,w,E]) like the reference."""
+        device.  Returns (out, logits [b*3,h,w,1,K], lq_feat [b*3,h,w,E]) like the reference.
+
+        frame_index (streaming, `pgtformer_b200/video.py`): device int32 [b*3]; x then holds DISTINCT frames and
+        clip frame f is x[frame_index[f]] — the per-frame work (BiSeNet, attention-free encoder levels) runs once per
+        distinct frame and its results are gathered into clip order, bit-identical to running it per clip."""
         a = self.arch
         x = x.to(self.dev, torch.float32).contiguous()
         Fr, _, H, W = x.shape
+        if frame_index is not None:
+            Fr = frame_index.numel()
         if Fr % a.tf != 0 or H % 64 != 0 or W % 64 != 0:
             raise ValueError('expected b*3 frames with H, W multiples of 64, got %s' % (tuple(x.shape),))
         hh, ww = H // 16, W // 16
@@ -465,7 +502,14 @@ class Engine:
         wd = self.w
         pos = self.parse_pos(x)
         # encoder
-        h, feats = self.encoder(x)
+        if frame_index is None:
+            h, feats = self.encoder(x)
+        else:
+            pos = self._gather(pos.view(x.shape[0], -1), frame_index).view(T, -1)
+            h, feats, lvl = self.encoder_frames(x)
+            # only the skip tensors the SFT fusion will read are worth moving (level 0 is 100 MB per clip and unused)
+            feats = [self._gather(f, frame_index) if (i in a.fuse_level_key and w > 0) else f for i, f in enumerate(feats)]
+            h, feats = self.encoder_clips(self._gather(h, frame_index), feats, lvl)
         h = h.view(T, -1)
         lq32 = self._lin(h, 'quant_conv', a.embed_dim, out_dtype=torch.float32)
         lq = self._lin(h, 'quant_conv', a.embed_dim)

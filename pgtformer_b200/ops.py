@@ -333,6 +333,36 @@ def upsample2x(x, out):
     return out
 
 
+def u8hwc_to_f32nchw(x_u8, out):
+    """rgb24 frames [F,H,W,3] uint8 -> fp32 [F,3,H,W] = (float)(v / 255.0), numpy's rounding (inference.py:6-10)."""
+    lib = L.load()
+    F, H, W, C = x_u8.shape
+    assert C == 3 and x_u8.dtype == torch.uint8 and x_u8.is_contiguous() and x_u8.is_cuda
+    assert out.dtype == torch.float32 and tuple(out.shape) == (F, 3, H, W) and out.is_contiguous()
+    L.check(lib.pgt_u8hwc_to_f32nchw(_p(x_u8), F, H, W, _p(out), _stream()))
+    return out
+
+
+def f32nchw_to_u8hwc(x, out_u8, first=0, step=1):
+    """uint8(clamp(x, 0, 1) * 255) of frames first, first+step, ... -> rgb24 [n,H,W,3] (inference.py:15-19)."""
+    lib = L.load()
+    n, H, W, C = out_u8.shape
+    assert C == 3 and out_u8.dtype == torch.uint8 and out_u8.is_contiguous()
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[1:] == (3, H, W) and first + (n - 1) * step < x.shape[0]
+    L.check(lib.pgt_f32nchw_to_u8hwc(_p(x), first, step, n, H, W, _p(out_u8), _stream()))
+    return out_u8
+
+
+def gather_frames(x, idx_i32, out):
+    """out[f] = x[idx[f]] along dim 0 (whole frames; idx: device int32)."""
+    lib = L.load()
+    assert x.is_contiguous() and out.is_contiguous() and x.dtype == out.dtype and x.shape[1:] == out.shape[1:]
+    assert idx_i32.dtype == torch.int32 and idx_i32.is_cuda and idx_i32.numel() == out.shape[0]
+    fb = x[0].numel() * x.element_size()
+    L.check(lib.pgt_gather_frames(_p(x), fb, _p(idx_i32), out.shape[0], _p(out), _stream()))
+    return out
+
+
 def copy2d(x, out):
     lib = L.load()
     T, C, ldx = _rows(x)
