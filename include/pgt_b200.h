@@ -136,12 +136,6 @@ int pgt_conv_rgb_bf16(const float* x_nchw, int F, int H, int W, int ksize, int s
                       const float* std3, const void* Wp, int ldw, int Cout, const float* bias, int act, void* out,
                       int ldo, float* gn_stats, void* stream);
 
-/* ---- first conv of the encoder: 3x3, Cin=3, fp32 NCHW input -> NHWC bf16 (direct FFMA kernel;
- * K = 27 is too small for the tensor pipe).  w: fp32 [Cout,3,3,3] (OIHW), bias fp32 [Cout].
- * Replaces Encoder.conv_in (archs/tdcrqvae3_arch.py:473-477,547). */
-int pgt_conv_in_rgb(const float* x_nchw, int F, int H, int W, const float* w, const float* bias, int Cout,
-                    void* y, int ldy, void* stream);
-
 /* ---- GroupNorm(32, eps) [+ SiLU] on NHWC bf16: y = act((x-mean)*rstd*gamma+beta).
  * `ws` is a caller-provided fp32 workspace of at least pgt_groupnorm_ws_floats(F, HW, C) floats.
  * Replaces Normalize()+nonlinearity (modules/rstt_layers.py:754-758,880-881,889-890) and
@@ -227,14 +221,11 @@ int pgt_adain(const void* q, int ldq, int q_dtype, const void* l, int ldl, int F
 
 /* ---- face-parsing branch (BiSeNet / ResNet18, archs/pgtformer_arch.py:34-397); its other convolutions run on
  * pgt_conv_bf16 / pgt_conv_up2x_bf16 / pgt_linear_bf16 with eval-mode BatchNorm folded into weights and bias.
- * pgt_stem7x7_rgb: conv 7x7 s2 p3 (3->64, BN folded, fp32 OIHW weights) + ReLU on the ImageNet-normalised image
- *   ((x-mean)/std fused into the load; mean/stdv are HOST pointers to 3 floats) -> bf16 [F,H/2,W/2,64]  (:91-94, :606)
+ * (the 7x7 stem is pgt_conv_rgb_bf16)
  * pgt_maxpool3x3s2: MaxPool2d(3, 2, 1) (:84,:94)        pgt_global_avgpool: F.avg_pool2d(x, x.size()[2:]) -> bf16 [F,C]
  * pgt_channel_affine: y = x * (scale[f,c] (+1)) + addv[f,c] + addm — ARM / FFM re-weighting (:203, :236-245, :331-333)
  * pgt_assemble_cond: bilinear(align_corners) resize of heads 0,1 to (h16,w16) + head 2, concatenated into the
  *   64-wide (57 used) conditioning map (:375-379). */
-int pgt_stem7x7_rgb(const float* x_nchw, int F, int H, int W, const float* mean, const float* stdv, const float* w,
-                    const float* bias, void* y, int ldy, void* stream);
 int pgt_maxpool3x3s2(const void* x, int ldx, int F, int H, int W, int C, void* y, int ldy, void* stream);
 int pgt_global_avgpool(const void* x, int ldx, int F, int HW, int C, void* y, int ldy, void* stream);
 int pgt_channel_affine(const void* x, int ldx, int F, int HW, int C, const void* scale, int lds, int plus_one,
@@ -243,8 +234,6 @@ int pgt_assemble_cond(const void* o0, int ld0, const void* o1, int ld1, const vo
                       int h16, int w16, int ncls, void* cond, int ldc, void* stream);
 
 /* ---- layout / elementwise helpers on NHWC bf16 */
-/* nearest x2 upsample [F,H,W,C] -> [F,2H,2W,C]  (F.interpolate in archs/tdcrqvae3_arch.py:48) */
-int pgt_upsample2x(const void* x, int ldx, int F, int H, int W, int C, void* y, int ldy, void* stream);
 /* strided copy of a [T, C] block (concat building: archs/pgtformer_arch.py:467-475) */
 int pgt_copy2d(const void* x, int ldx, int T, int C, void* y, int ldy, void* stream);
 /* temporal regroup for the SFT block's cross-frame 1x1 mixers (archs/pgtformer_arch.py:467-472):

@@ -1,50 +1,10 @@
-// Layout conversion and small data-movement kernels (HBM-bound, 128-bit vectorised) plus the direct
-// 3-channel first convolution.
+// Layout conversion and small data-movement kernels (HBM-bound, 128-bit vectorised), and the streaming video
+// front / back end.
 #include <algorithm>
 
 #include "common.cuh"
 
 namespace pgt {
-
-// nearest x2: each thread reads one 16-byte vector of a SOURCE pixel and writes it to its four destinations
-// (two source vectors in flight per thread).
-__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int F, int H, int W, int C,
-                                  __nv_bfloat16* __restrict__ y, int ldy) {
-  const int vc = C >> 3;
-  const size_t total = (size_t)F * H * W * vc;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  auto one = [&](size_t i, uint4& u, size_t& dst) {
-    const int v = (int)(i % vc);
-    size_t pix = i / vc;
-    const int sx = (int)(pix % W); pix /= W;
-    const int sy = (int)(pix % H);
-    const int f = (int)(pix / H);
-    u = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)f * H + sy) * W + sx) * ldx) + v);
-    dst = (((size_t)f * 2 * H + 2 * sy) * 2 * W + 2 * sx) * ldy + (size_t)v * 8;
-  };
-  auto put = [&](const uint4& u, size_t dst) {
-    const size_t row = (size_t)2 * W * ldy;
-    *reinterpret_cast<uint4*>(y + dst) = u;
-    *reinterpret_cast<uint4*>(y + dst + ldy) = u;
-    *reinterpret_cast<uint4*>(y + dst + row) = u;
-    *reinterpret_cast<uint4*>(y + dst + row + ldy) = u;
-  };
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; i + stride < total; i += 2 * stride) {
-    uint4 u0, u1;
-    size_t d0, d1;
-    one(i, u0, d0);
-    one(i + stride, u1, d1);
-    put(u0, d0);
-    put(u1, d1);
-  }
-  if (i < total) {
-    uint4 u0;
-    size_t d0;
-    one(i, u0, d0);
-    put(u0, d0);
-  }
-}
 
 __global__ void copy2d_kernel(const __nv_bfloat16* __restrict__ x, int ldx, size_t T, int C,
                               __nv_bfloat16* __restrict__ y, int ldy) {
@@ -116,65 +76,6 @@ __global__ void nhwc_to_f32_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
   }
 }
 
-// Encoder conv_in: 3x3, 3 -> Cout channels, fp32 math on the fp32 image.  One thread = one pixel x all Cout
-// channels (16 at a time): every lane of a warp reads the SAME weight vector from shared memory (pure broadcast,
-// 1 wavefront per 128-bit read), inputs are coalesced along x, outputs are 32-byte bf16 stores.
-__global__ void __launch_bounds__(256)
-conv_in_rgb_kernel(const float* __restrict__ x, int H, int W, const float* __restrict__ w, const float* __restrict__ bias,
-                   int Cout, __nv_bfloat16* __restrict__ y, int ldy) {
-  extern __shared__ __align__(16) float sw[];          // [27][Cout] + bias[Cout]
-  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
-    const int k = i / Cout, co = i % Cout;           // k = ci*9 + dy*3 + dx  (OIHW -> [k][co])
-    sw[i] = w[co * 27 + k];
-  }
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = bias[i];
-  __syncthreads();
-  const int f = blockIdx.z;
-  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= (size_t)H * W) return;
-  const int py = (int)(pix / W), px = (int)(pix % W);
-  float in[27];
-#pragma unroll
-  for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const int yy = py + dy - 1, xx = px + dx - 1;
-        in[ci * 9 + dy * 3 + dx] = (yy >= 0 && yy < H && xx >= 0 && xx < W)
-                                       ? __ldg(x + (((size_t)f * 3 + ci) * H + yy) * W + xx) : 0.f;
-      }
-  __nv_bfloat16* orow = y + ((size_t)f * H * W + pix) * ldy;
-  for (int g = 0; g < (Cout >> 4); ++g) {
-    float acc[16];
-    const float4* bp = reinterpret_cast<const float4*>(sw + 27 * Cout + g * 16);
-#pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4) {
-      const float4 b = bp[j4];
-      acc[4 * j4] = b.x; acc[4 * j4 + 1] = b.y; acc[4 * j4 + 2] = b.z; acc[4 * j4 + 3] = b.w;
-    }
-#pragma unroll
-    for (int k = 0; k < 27; ++k) {
-      const float4* wk = reinterpret_cast<const float4*>(sw + k * Cout + g * 16);
-#pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4) {
-        const float4 wv = wk[j4];
-        acc[4 * j4 + 0] = fmaf(in[k], wv.x, acc[4 * j4 + 0]);
-        acc[4 * j4 + 1] = fmaf(in[k], wv.y, acc[4 * j4 + 1]);
-        acc[4 * j4 + 2] = fmaf(in[k], wv.z, acc[4 * j4 + 2]);
-        acc[4 * j4 + 3] = fmaf(in[k], wv.w, acc[4 * j4 + 3]);
-      }
-    }
-    uint4 u0, u1;
-    u0.x = pack_bf16x2(acc[0], acc[1]); u0.y = pack_bf16x2(acc[2], acc[3]);
-    u0.z = pack_bf16x2(acc[4], acc[5]); u0.w = pack_bf16x2(acc[6], acc[7]);
-    u1.x = pack_bf16x2(acc[8], acc[9]); u1.y = pack_bf16x2(acc[10], acc[11]);
-    u1.z = pack_bf16x2(acc[12], acc[13]); u1.w = pack_bf16x2(acc[14], acc[15]);
-    uint4* o = reinterpret_cast<uint4*>(orow + g * 16);
-    o[0] = u0; o[1] = u1;
-  }
-}
-
 }  // namespace pgt
 
 using namespace pgt;
@@ -183,16 +84,6 @@ static int ew_grid(size_t total, int threads) {
   size_t b = (total + threads - 1) / threads;
   const size_t cap = (size_t)num_sms() * 32;
   return (int)(b < cap ? (b ? b : 1) : cap);
-}
-
-extern "C" int pgt_upsample2x(const void* x, int ldx, int F, int H, int W, int C, void* y, int ldy, void* stream) {
-  PGT_CHECK_ARG(x && y && F > 0 && H > 0 && W > 0 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0);
-  ProfScope ps(PGT_PROF_MOVE, 5.0 * F * (double)H * W * C * 2, static_cast<cudaStream_t>(stream), "pgt_upsample2x");
-  const size_t total = (size_t)F * H * W * (C / 8) / 2 + 1;
-  upsample2x_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), ldx, F, H, W, C, reinterpret_cast<__nv_bfloat16*>(y), ldy);
-  PGT_LAUNCH_OK();
-  return PGT_OK;
 }
 
 extern "C" int pgt_copy2d(const void* x, int ldx, int T, int C, void* y, int ldy, void* stream) {
@@ -222,18 +113,6 @@ extern "C" int pgt_nhwc_bf16_to_f32(const void* x, int ldx, int F, int HW, int C
   dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), F);
   nhwc_to_f32_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C, y, to_nchw);
-  PGT_LAUNCH_OK();
-  return PGT_OK;
-}
-
-extern "C" int pgt_conv_in_rgb(const float* x_nchw, int F, int H, int W, const float* w, const float* bias, int Cout,
-                               void* y, int ldy, void* stream) {
-  PGT_CHECK_ARG(x_nchw && w && bias && y && F > 0 && H > 0 && W > 0 && Cout % 16 == 0 && Cout <= 128 && ldy % 8 == 0);
-  ProfScope ps(PGT_PROF_MOVE, (double)F * H * W * (12.0 + 2.0 * Cout), static_cast<cudaStream_t>(stream), "pgt_conv_in_rgb");
-  const size_t threads = (size_t)H * W;
-  dim3 grid((unsigned)((threads + 255) / 256), 1, F);
-  conv_in_rgb_kernel<<<grid, 256, (27 * Cout + Cout) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      x_nchw, H, W, w, bias, Cout, reinterpret_cast<__nv_bfloat16*>(y), ldy);
   PGT_LAUNCH_OK();
   return PGT_OK;
 }

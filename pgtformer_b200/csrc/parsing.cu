@@ -1,8 +1,8 @@
 // Kernels specific to the face-parsing branch (BiSeNet / ResNet18, archs/pgtformer_arch.py:34-397 in the
-// reference): the 7x7 stride-2 RGB stem, 3x3 stride-2 max-pool, global average pool, per-(frame,channel)
+// reference): 3x3 stride-2 max-pool, global average pool, per-(frame,channel)
 // attention re-weighting, and the bilinear(align_corners) assembly of the three 19-class heads into the
-// 57(+7 pad)-channel conditioning map.  All the other convolutions of the branch run on the tcgen05
-// implicit-GEMM kernel with BatchNorm folded into weights / bias.
+// 57(+7 pad)-channel conditioning map.  Every convolution of the branch (the 7x7 stem included) runs on the tcgen05
+// kernels with BatchNorm folded into weights / bias.
 #include <float.h>
 
 #include "common.cuh"
@@ -19,70 +19,6 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {
   u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
   u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
   *reinterpret_cast<uint4*>(p) = u;
-}
-
-// ------------------------------------------------------------------------------ 7x7 s2 p3 stem (3 -> 64) + ReLU
-// Block = 16x16 output pixels; the normalised (x-mean)/std input patch (37x37x3) and the BN-folded weights
-// [147][64] live in shared memory; a thread owns one pixel and all 64 channels (weights are warp-broadcast).
-constexpr int STEM_T = 16, STEM_IN = 2 * STEM_T + 5, STEM_CO = 64;
-__global__ void __launch_bounds__(256)
-stem7x7_kernel(const float* __restrict__ x, int H, int W, float m0, float m1, float m2, float s0, float s1, float s2,
-               const float* __restrict__ w, const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int ldy) {
-  extern __shared__ __align__(16) float sm[];
-  float* sw = sm;                                   // [147][64]
-  float* sb = sw + 147 * STEM_CO;                   // [64]
-  float* sin = sb + STEM_CO;                        // [3][37][37]
-  const int Ho = H >> 1, Wo = W >> 1;
-  const int f = blockIdx.z;
-  const int oy0 = blockIdx.y * STEM_T, ox0 = blockIdx.x * STEM_T;
-  for (int i = threadIdx.x; i < 147 * STEM_CO; i += 256) {
-    const int k = i / STEM_CO, co = i % STEM_CO;    // k = ci*49 + ky*7 + kx   (OIHW -> [k][co])
-    sw[i] = w[co * 147 + k];
-  }
-  if (threadIdx.x < STEM_CO) sb[threadIdx.x] = bias[threadIdx.x];
-  const float mean[3] = {m0, m1, m2}, istd[3] = {1.f / s0, 1.f / s1, 1.f / s2};
-  for (int i = threadIdx.x; i < 3 * STEM_IN * STEM_IN; i += 256) {
-    const int ci = i / (STEM_IN * STEM_IN), rem = i % (STEM_IN * STEM_IN);
-    const int iy = 2 * oy0 - 3 + rem / STEM_IN, ix = 2 * ox0 - 3 + rem % STEM_IN;
-    float v = 0.f;                                  // zero padding is applied AFTER normalisation (reference order)
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = (__ldg(x + (((size_t)f * 3 + ci) * H + iy) * W + ix) - mean[ci]) * istd[ci];
-    sin[i] = v;
-  }
-  __syncthreads();
-  const int ty = threadIdx.x / STEM_T, tx = threadIdx.x % STEM_T;
-  const int oy = oy0 + ty, ox = ox0 + tx;
-  float acc[STEM_CO];
-#pragma unroll
-  for (int j = 0; j < STEM_CO; ++j) acc[j] = sb[j];
-  for (int ci = 0; ci < 3; ++ci) {
-    for (int ky = 0; ky < 7; ++ky) {
-      float in[7];
-#pragma unroll
-      for (int kx = 0; kx < 7; ++kx) in[kx] = sin[(ci * STEM_IN + 2 * ty + ky) * STEM_IN + 2 * tx + kx];
-#pragma unroll
-      for (int kx = 0; kx < 7; ++kx) {
-        const float4* wk = reinterpret_cast<const float4*>(sw + (ci * 49 + ky * 7 + kx) * STEM_CO);
-#pragma unroll
-        for (int j4 = 0; j4 < STEM_CO / 4; ++j4) {
-          const float4 wv = wk[j4];
-          acc[4 * j4 + 0] = fmaf(in[kx], wv.x, acc[4 * j4 + 0]);
-          acc[4 * j4 + 1] = fmaf(in[kx], wv.y, acc[4 * j4 + 1]);
-          acc[4 * j4 + 2] = fmaf(in[kx], wv.z, acc[4 * j4 + 2]);
-          acc[4 * j4 + 3] = fmaf(in[kx], wv.w, acc[4 * j4 + 3]);
-        }
-      }
-    }
-  }
-  if (oy < Ho && ox < Wo) {
-    __nv_bfloat16* o = y + (((size_t)f * Ho + oy) * Wo + ox) * ldy;
-#pragma unroll
-    for (int q = 0; q < STEM_CO / 8; ++q) {
-      float v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaxf(acc[q * 8 + j], 0.f);
-      st8(o + q * 8, v);
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------ 3x3 s2 p1 max-pool
@@ -217,26 +153,6 @@ static int grid_for(size_t total, int threads) {
   size_t b = (total + threads - 1) / threads;
   const size_t cap = (size_t)num_sms() * 32;
   return (int)(b < cap ? (b ? b : 1) : cap);
-}
-
-extern "C" int pgt_stem7x7_rgb(const float* x_nchw, int F, int H, int W, const float* mean, const float* stdv,
-                               const float* w, const float* bias, void* y, int ldy, void* stream) {
-  PGT_CHECK_ARG(x_nchw && mean && stdv && w && bias && y && F > 0 && H > 0 && W > 0 && (H % 2) == 0 && (W % 2) == 0 &&
-                ldy % 8 == 0 && ldy >= STEM_CO);
-  const size_t smem = (147 * STEM_CO + STEM_CO + 3 * STEM_IN * STEM_IN) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    PGT_CUDA_OK(cudaFuncSetAttribute(stem7x7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  ProfScope ps(PGT_PROF_MOVE, (double)F * H * W * 12.0 + (double)F * (H / 2) * (W / 2) * 128.0, st, "stem7x7");
-  dim3 grid(ceil_div(W / 2, STEM_T), ceil_div(H / 2, STEM_T), F);
-  // mean / std are passed by value: they are 3 host floats
-  stem7x7_kernel<<<grid, 256, smem, st>>>(x_nchw, H, W, mean[0], mean[1], mean[2], stdv[0], stdv[1], stdv[2], w, bias,
-                                          reinterpret_cast<__nv_bfloat16*>(y), ldy);
-  PGT_LAUNCH_OK();
-  return PGT_OK;
 }
 
 extern "C" int pgt_maxpool3x3s2(const void* x, int ldx, int F, int H, int W, int C, void* y, int ldy, void* stream) {

@@ -123,15 +123,6 @@ def conv_up2x(x, wp4, cout, out, bias=None, act=ACT_NONE, gn_stats=None):
     return out
 
 
-def conv_in_rgb(x_nchw, w, bias, out):
-    lib = L.load()
-    F, C, H, W = x_nchw.shape
-    assert C == 3 and x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
-    assert w.dtype == torch.float32 and w.is_contiguous() and bias.dtype == torch.float32
-    L.check(lib.pgt_conv_in_rgb(_p(x_nchw), F, H, W, _p(w), _p(bias), w.shape[0], _p(out), _rows(out)[2], _stream()))
-    return out
-
-
 _gn_ws = {}
 
 
@@ -283,17 +274,6 @@ def adain(q, style, out, eps=1e-5):
     return out
 
 
-def stem7x7(x_nchw, mean3, std3, w, bias, out):
-    """mean3 / std3: python sequences of 3 floats (host)."""
-    lib = L.load()
-    F, C, H, W = x_nchw.shape
-    assert C == 3 and x_nchw.dtype == torch.float32 and x_nchw.is_contiguous() and w.is_contiguous()
-    m = (ctypes.c_float * 3)(*[float(v) for v in mean3])
-    s = (ctypes.c_float * 3)(*[float(v) for v in std3])
-    L.check(lib.pgt_stem7x7_rgb(_p(x_nchw), F, H, W, m, s, _p(w), _p(bias), _p(out), _rows(out)[2], _stream()))
-    return out
-
-
 def maxpool3x3s2(x, out):
     lib = L.load()
     F, H, W, C = x.shape
@@ -324,13 +304,6 @@ def assemble_cond(o0, o1, o2, cond, ncls=19):
     L.check(lib.pgt_assemble_cond(_p(o0), _rows(o0)[2], _p(o1), _rows(o1)[2], _p(o2), _rows(o2)[2], F, h8, w8, h16, w16,
                                   ncls, _p(cond), _rows(cond)[2], _stream()))
     return cond
-
-
-def upsample2x(x, out):
-    lib = L.load()
-    F, H, W, C = x.shape
-    L.check(lib.pgt_upsample2x(_p(x), _rows(x)[2], F, H, W, C, _p(out), _rows(out)[2], _stream()))
-    return out
 
 
 def u8hwc_to_f32nchw(x_u8, out):

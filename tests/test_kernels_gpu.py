@@ -209,15 +209,6 @@ def test_conv_up2x_folded(Fr, H, W, C):
     check_close(out, ref, 'conv up2x', bf16_out=True, rel=6e-3)
 
 
-def test_conv_in_rgb():
-    o = ops()
-    x = torch.rand(3, 3, 32, 32, generator=torch.Generator().manual_seed(40))
-    w, b = rnd((64, 3, 3, 3), 41, 27 ** -0.5), rnd((64,), 42, 0.1)
-    out = torch.empty(3, 32, 32, 64, dtype=torch.bfloat16, device=DEV)
-    o.conv_in_rgb(x.to(DEV), w.to(DEV), b.to(DEV), out)
-    check_close(out, F.conv2d(x, w, b, padding=1).permute(0, 2, 3, 1), 'conv_in', bf16_out=True)
-
-
 # ------------------------------------------------------------------------------------ norms
 @pytest.mark.parametrize('Fr,HW,C', [(3, 64, 64), (3, 1024, 512), (2, 4096, 128), (3, 256, 1056), (3, 1024, 288), (3, 64, 544)])
 def test_groupnorm_silu(Fr, HW, C):
@@ -370,9 +361,6 @@ def test_layout_kernels():
     check_close(y[..., :3], ref, 'nchw->nhwc', bf16_out=True)
     assert y[..., 3:].abs().max() == 0
     a = bf(rnd((2, 8, 8, 64), 121))
-    up = torch.empty(2, 16, 16, 64, dtype=torch.bfloat16, device=DEV)
-    o.upsample2x(a.to(DEV), up)
-    assert torch.equal(up.cpu(), F.interpolate(a.float().permute(0, 3, 1, 2), scale_factor=2.0, mode='nearest').permute(0, 2, 3, 1).to(torch.bfloat16))
     buf = torch.zeros(2, 8, 8, 160, dtype=torch.bfloat16, device=DEV)
     o.copy2d(a.to(DEV), buf[..., 64:128])
     assert torch.equal(buf[..., 64:128].cpu(), a) and buf[..., :64].abs().max() == 0
@@ -385,17 +373,10 @@ def test_layout_kernels():
 
 
 # ------------------------------------------------------------------------------------ parsing-branch kernels
-def test_stem7x7_maxpool_avgpool_affine_assemble():
+def test_maxpool_avgpool_affine_assemble():
     o = ops()
     Fr, H, W = 3, 64, 64
-    x = torch.rand(Fr, 3, H, W, generator=torch.Generator().manual_seed(130))
-    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
-    w, b = rnd((64, 3, 7, 7), 131, 147 ** -0.5), rnd((64,), 132, 0.1)
-    y = torch.empty(Fr, H // 2, W // 2, 64, dtype=torch.bfloat16, device=DEV)
-    o.stem7x7(x.to(DEV), mean, std, w.to(DEV), b.to(DEV), y)
-    nx = (x - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
-    ref = F.relu(F.conv2d(nx, w, b, stride=2, padding=3)).permute(0, 2, 3, 1)
-    check_close(y, ref, 'stem7x7', bf16_out=True)
+    y = bf(rnd((Fr, H // 2, W // 2, 64), 130)).to(DEV)
     mp = torch.empty(Fr, H // 4, W // 4, 64, dtype=torch.bfloat16, device=DEV)
     o.maxpool3x3s2(y, mp)
     refmp = F.max_pool2d(y.float().cpu().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
