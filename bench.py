@@ -28,6 +28,17 @@ if ROOT not in sys.path:
 FLOPS_PER_CLIP = {128: 236.8e9, 256: None, 512: 3952.0e9, 1024: 17895.0e9}     # SURVEY 8(d), 2*MAC
 
 
+def config_label(b, H, world):
+    """Which BASELINE.json config this run is (configs[2] / [3] are the ones the metric is quoted on)."""
+    if H == 512 and b == 16:
+        return 'BASELINE configs[2]' if world == 1 else 'BASELINE configs[3] shape: 16 clips/GPU, weak scaling'
+    if H == 512 and b == 1 and world == 1:
+        return 'BASELINE configs[1]'
+    if H == 1024:
+        return 'BASELINE configs[4] shape (1024x1024 clips)'
+    return 'custom size, not a BASELINE config'
+
+
 def flops_per_clip(H):
     s = H / 512.0
     return (3952.0e9 - 173.9e9) * s * s + 173.9e9 * s ** 4
@@ -262,8 +273,8 @@ def main():
             'metric': 'clips_per_s', 'value': value, 'unit': 'clips/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-            'config': {'workload': 'PGTFormer.forward on %d clips/GPU of 3x%dx%d (BASELINE configs[%s]), w=1, adain, '
-                                   'random-init pgtformer-base' % (b, H, H, '2' if world == 1 else '3'),
+            'config': {'workload': 'PGTFormer.forward on %d clips/GPU of 3x%dx%d (%s), w=1, adain, '
+                                   'random-init pgtformer-base' % (b, H, H, config_label(b, H, world)),
                        'clips_per_gpu': b, 'size': H, 'global_clips': world * b, 'parallelism': 'dp%d' % world,
                        'l2_policy': 'inputs and activations (GBs per step) exceed the 126 MB L2; no flush needed',
                        'flops_per_clip': flops_per_clip(H), 'cuda_graph': bool(args.graph)},
