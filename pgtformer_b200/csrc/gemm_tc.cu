@@ -2,16 +2,22 @@
 //
 //   out[rows, N] = epilogue( A[rows, K] * W[N, K]^T )          bf16 operands, fp32 accumulate in TMEM
 //
-// One persistent, warp-specialised kernel (320 threads):
+// Persistent, warp-specialised kernels (352 threads; + 128 in the GroupNorm-fused halo variant):
 //   warp 0      TMA producer: A tile (128 rows x 64 K) and W tile (BN rows x 64 K) per k-block, 128B swizzle
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, cta_group::1)
+//   warp 1      TMEM allocator; ONE elected lane walks the whole k loop of a tile (barrier waits included) and issues
+//               tcgen05.mma 128 x BN x 16 — cta_group::2 (M = 256 over a CTA pair, each CTA holding half of every
+//               weight tile) in the PAIR / halo2 kernels
 //   warps 2..9  epilogue, two warps per TMEM lane quadrant (each half-group of 4 warps owns half of the tile's
-//               column panels): tcgen05.ld -> +bias (smem) -> activation -> +residual -> bf16/fp32 pack into a
-//               128B-swizzled smem staging panel -> TMA store.  The residual panel is TMA-loaded INTO the
-//               staging slot ahead of time, so both the residual read and the output write are full-line,
-//               coalesced bulk copies issued by one thread.
-// Pipelines: smem full/empty ring (TMA <-> MMA) and a 2-deep TMEM accumulator ring (MMA <-> epilogue), so
-// the epilogue of tile i overlaps the main loop of tile i+1.
+//               column panels): tcgen05.ld -> +bias -> activation -> +residual / SFT from the staging slot ->
+//               optional GroupNorm partial statistics -> bf16/fp32 pack into a 128B-swizzled smem staging panel
+//   warp 10     epilogue DMA: TMA-loads the residual (/ SFT scale) panel INTO the staging slot ahead of time and
+//               TMA-stores the finished panel, so both are full-line bulk copies and no CTA barrier sits on the path
+// Pipelines: smem full/empty ring (TMA <-> MMA), a 2-deep TMEM accumulator ring (MMA <-> epilogue) and a 4-slot
+// staging ring (epilogue <-> DMA warp), so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Kernels in this file: gemm_tc_kernel<BN, PAIR> (linear / generic implicit-GEMM conv), conv_halo_kernel<BN, GN>
+// (3x3 and upsample-phase convs with Cout <= 128: one halo slab serves every tap), conv_halo2_kernel<BN> (the same on
+// CTA pairs).
 //
 // The A operand is produced by TMA in three addressing modes:
 //   LINEAR   2-D map [K, rows]
