@@ -527,7 +527,8 @@ def test_conv_with_fused_input_groupnorm(Fr, H, W, Cin, Cout, res, nchw, fused_s
     w = pack_conv_weight(bf(rnd((Cout, Cin, 3, 3), 193, (9 * Cin) ** -0.5)).float()).to(DEV)
     b = rnd((Cout,), 194, 0.1).to(DEV)
     r = bf(rnd((Fr, H, W, Cout), 195)).to(DEV) if res else None
-    assert o.conv_gn_supported(H, W, Cin, Cout)
+    if not o.conv_gn_supported(H, W, Cin, Cout):
+        pytest.skip('halo-reuse conv disabled (PGT_NO_HALO): the fused-GroupNorm variant does not exist')
 
     def mk():
         return (torch.empty(Fr, Cout, H, W, dtype=torch.float32, device=DEV) if nchw
