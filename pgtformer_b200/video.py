@@ -59,6 +59,12 @@ class VideoRestorer:
         n = len(local_windows)
         return ops.f32nchw_to_u8hwc(out, torch.empty(n, H, W, 3, dtype=torch.uint8, device=x.device), first=1, step=3)
 
+    def _run_batch(self, frames_u8, local_windows):
+        """Host uint8 [Fd,H,W,3] + window index triples -> host uint8 [count,H,W,3] (synchronous; `stream()` uses it)."""
+        dev = self.model.engine().dev
+        d = torch.from_numpy(np.ascontiguousarray(frames_u8)).pin_memory().to(dev, non_blocking=True)
+        return self._enqueue(d, local_windows).cpu().numpy()
+
     # ------------------------------------------------------------------ whole sequence in memory
     @torch.no_grad()
     def restore(self, frames_u8):
@@ -130,11 +136,8 @@ class VideoRestorer:
             n_known = total_in
             lo = max(emitted - 1, 0)
             hi = min(emitted + cnt, n_known - 1)
-            host = torch.from_numpy(np.stack(buf[lo - base:hi - base + 1])).pin_memory()
-            dev = self.model.engine().dev
-            d = host.to(dev, non_blocking=True)
             local = [(max(i - 1, 0) - lo, i - lo, min(i + 1, n_known - 1) - lo) for i in range(emitted, emitted + cnt)]
-            res = self._enqueue(d, local).cpu().numpy()
+            res = self._run_batch(np.stack(buf[lo - base:hi - base + 1]), local)
             for k in range(cnt):
                 yield res[k]
             emitted += cnt

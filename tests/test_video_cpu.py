@@ -32,3 +32,38 @@ def test_conversion_oracles_follow_numpy_semantics():
     assert np.array_equal(t[1, 2], (fr[1, :, :, 2] / 255.0).astype(np.float32))
     x = np.array([[-0.2, 0.0, 0.5, 0.9999, 1.0, 1.7]], np.float32).repeat(3, 0).reshape(3, 1, 6)
     assert VO.tensor2rgb(x)[0, :, 0].tolist() == [0, 0, 127, 254, 255, 255]
+
+
+class _FakeRestorer:
+    """VideoRestorer.stream() with the device work replaced by a window function that identifies its three frames."""
+
+    def __new__(cls, batch):
+        from pgtformer_b200.video import VideoRestorer
+        vr = VideoRestorer(model=None, clips_per_batch=batch)
+        vr.batches = []
+
+        def run_batch(frames_u8, local_windows):
+            vr.batches.append((frames_u8.shape[0], len(local_windows)))
+            return np.stack([_mix([frames_u8[a], frames_u8[b], frames_u8[c]]) for a, b, c in local_windows])
+        vr._run_batch = run_batch
+        return vr
+
+
+def _mix(win):
+    return (win[0].astype(np.int64) * 5 + win[1].astype(np.int64) * 11 + win[2].astype(np.int64) * 17).astype(np.int64)
+
+
+@pytest.mark.parametrize('n', [0, 1, 2, 3, 5, 16, 17, 18, 41])
+@pytest.mark.parametrize('batch', [1, 2, 16])
+def test_stream_bookkeeping_matches_reference_loop(n, batch):
+    """Iterator in, iterator out: every window is emitted once, in order, from exactly the frames the reference's
+    three-slot buffer would hold — across batch boundaries, buffer trimming and the duplicated end frames."""
+    frames = [np.full((2, 2, 3), (7 * i + 1) % 251, np.uint8) for i in range(n)]
+    vr = _FakeRestorer(batch)
+    got = list(vr.stream(iter(frames)))
+    want = VO.restore_frames(frames, _mix)
+    assert len(got) == len(want) == n
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    # bounded memory: a batch never ships more than its windows + the two neighbours
+    assert all(fd <= cnt + 2 and cnt <= batch for fd, cnt in vr.batches)
