@@ -70,6 +70,8 @@ int pgt_version(void);
  * `gpu_launches` claim). */
 int64_t pgt_launch_count(void);
 void pgt_reset_launch_count(void);
+/* CUtensorMap cache (one encode per distinct (pointer, shape, box) for the life of the process): hit / miss counters. */
+void pgt_tmap_cache_stats(int64_t* hits, int64_t* misses);
 
 /* Optional per-launch profiler (bench.py's roofline figures): between begin and end every launch of
  * the classes below is bracketed by CUDA events on its own stream; end() synchronises and returns,
@@ -190,6 +192,15 @@ int pgt_swin_mlp_bf16(const void* x, int ldx, int T, int C, const float* ln_g, c
 int pgt_window_attention(const void* qkv, int ldqkv, int clips, int H, int W, int C, int heads, int shift,
                          const float* bias_tab, void* out, int ldo, void* stream);
 
+/* The same core on TMA + tcgen05 (window_attn_tc.cu): a window's q / k / v rows of a 64-column chunk are one 5-D TMA box
+ * of the qkv matrix (wrapped windows of a shifted block: 2 or 4 partial boxes), QK^T and PV run as tcgen05.mma with S / O
+ * in TMEM, results leave through TMA stores of the same boxes.  tab: fp16 [4][heads][6][48][8] bias / mask tables
+ * (pgtformer_b200/ops.py::window_tables — relative-position bias and the {0,-100} shift mask in the row order of the
+ * four box layouts, times log2 e).  mode_n64: for d = 32 run P V with N = 64 instead of a half-atom N = 32 operand view.
+ * Returns PGT_ERR_UNSUPPORTED unless heads == 8, d in {32, 64}, C % 128 == 0, shift in {0, 2}. */
+int pgt_window_attention_tc(const void* qkv, int ldqkv, int clips, int H, int W, int C, int heads, int shift,
+                            const void* tab, void* out, int ldo, int mode_n64, void* stream);
+
 /* ---- global multi-head attention (flash-attention forward, no mask), per clip:
  * q,k,v: bf16 [clips*L, ld*] with head h at columns [h*d, (h+1)*d); out bf16 [clips*L, ldo].
  * Replaces the nn.MultiheadAttention core (archs/codeformer_arch.py:105,129-130); the
@@ -212,6 +223,17 @@ int pgt_argmax_gather(const float* logits, int T, int K, const float* codebook, 
                       int64_t* idx, void* quant, int ldq, int quant_dtype, void* stream);
 int pgt_l2_argmin(const float* z, int T, int E, const float* codebook, int K, int64_t* idx, float* quant,
                   void* stream);
+/* The same result on tcgen05 (l2_argmin_tc.cu): bf16 tensor-core scores of all K codes + a rigorous error window
+ * around the approximate minimum; the window's members are re-evaluated exactly (fp32, fp64 when closer than the fp32
+ * bound), tokens whose window does not fit go through the exhaustive kernel above — equal to an fp64 argmin with
+ * first-index tie-break for every input.
+ *   pgt_codebook_pack (load time): cb_bf16 [K, E] bf16 copy, cb_norm [K + 2] fp32 = ||e_k||^2, max||e~||^2, max||e - e~||^2.
+ *   workspace: int32 [pgt_l2_argmin_ws_ints(T)] scratch (fallback list + per-token candidate lists).
+ *   Returns PGT_ERR_UNSUPPORTED unless K % 256 == 0, E % 128 == 0, E <= 512 (callers then use pgt_l2_argmin). */
+int pgt_codebook_pack(const float* codebook, int K, int E, void* cb_bf16, float* cb_norm, void* stream);
+int64_t pgt_l2_argmin_ws_ints(int T);
+int pgt_l2_argmin_tc(const float* z, int T, int E, const float* codebook, const void* cb_bf16, const float* cb_norm,
+                     int K, int64_t* idx, float* quant, int32_t* workspace, void* stream);
 
 /* ---- AdaIN: y = (q - mean_q)/std_q * std_l + mean_l per (frame, channel) over HW, unbiased
  * variance + eps.  q: bf16/fp32 [F, HW, ldq]; l (style) bf16 [F, HW, ldl]; y bf16.

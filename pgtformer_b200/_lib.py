@@ -30,6 +30,7 @@ SIGNATURES = {
     'pgt_version': (c_int, []),
     'pgt_launch_count': (c_int64, []),
     'pgt_reset_launch_count': (None, []),
+    'pgt_tmap_cache_stats': (None, [c_void_p, c_void_p]),
     'pgt_profile_begin': (c_int, []),
     'pgt_profile_end': (c_int, [c_void_p, c_void_p, c_void_p]),
     'pgt_profile_end_csv': (c_int, [c_char_p, c_void_p, c_void_p, c_void_p]),
@@ -59,11 +60,17 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     'pgt_window_attention': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                      c_int, c_void_p]),
+    'pgt_window_attention_tc': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                        c_int, c_int, c_void_p]),
     'pgt_mha_fwd': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                             c_int, c_void_p]),
     'pgt_argmax_gather': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                   c_int, c_void_p]),
     'pgt_l2_argmin': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    'pgt_codebook_pack': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'pgt_l2_argmin_ws_ints': (c_int64, [c_int]),
+    'pgt_l2_argmin_tc': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                 c_void_p, c_void_p]),
     'pgt_adain': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int,
                           c_void_p]),
     'pgt_maxpool3x3s2': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "tmap.cuh"
 
 namespace pgt {
 static thread_local char g_last_error[512] = "";
@@ -15,15 +16,29 @@ void set_cuda_error(cudaError_t e, const char* where) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int num_sms() {
-  static int n = 0;
+  static std::atomic<int> per_dev[64];                 // per device: a process may drive several GPUs
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = per_dev[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    per_dev[dev].store(n, std::memory_order_relaxed);
   }
   return n;
 }
+
+// ---- tensor-map cache (tmap.cuh)
+static std::atomic<long long> g_tmap_hits{0}, g_tmap_misses{0};
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash>& tmap_cache() {
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> c;
+  return c;
+}
+std::mutex& tmap_cache_mutex() {
+  static std::mutex m;
+  return m;
+}
+void tmap_cache_count(bool hit) { (hit ? g_tmap_hits : g_tmap_misses).fetch_add(1, std::memory_order_relaxed); }
+void tmap_cache_stats(long long* hits, long long* misses) { *hits = g_tmap_hits.load(); *misses = g_tmap_misses.load(); }
 
 // ---- optional per-launch profiler: CUDA events on the launching stream around every launch of a class
 struct ProfRec { cudaEvent_t e0, e1; int cls; double work; char desc[96]; };
@@ -81,6 +96,12 @@ extern "C" const char* pgt_strerror(int status) {
   }
 }
 extern "C" const char* pgt_last_cuda_error(void) { return pgt::g_last_error; }
-extern "C" int pgt_version(void) { return 100; }
+extern "C" int pgt_version(void) { return 200; }
+extern "C" void pgt_tmap_cache_stats(int64_t* hits, int64_t* misses) {
+  long long h = 0, m = 0;
+  pgt::tmap_cache_stats(&h, &m);
+  if (hits) *hits = h;
+  if (misses) *misses = m;
+}
 extern "C" int64_t pgt_launch_count(void) { return pgt::g_launches.load(); }
 extern "C" void pgt_reset_launch_count(void) { pgt::g_launches.store(0); }

@@ -86,9 +86,13 @@ __device__ __forceinline__ void cand_insert(Cand (&top)[AM_TOP], float v, int i)
   }
 }
 
+// Exhaustive and exact: every code is scored in fp32 (direct sum of squared differences), the per-token top-4 is
+// re-evaluated in fp64.  Runs on all T tokens (list == nullptr), or on the tokens `list[0 .. *count)` that the
+// tcgen05 kernel (l2_argmin_tc.cu) could not certify — normally none, then every CTA returns at once.
 __global__ void __launch_bounds__(256)
 l2_argmin_kernel(const float* __restrict__ z, int T, int E, const float* __restrict__ cb, int K,
-                 int64_t* __restrict__ idx, float* __restrict__ quant) {
+                 int64_t* __restrict__ idx, float* __restrict__ quant, const int* __restrict__ list,
+                 const int* __restrict__ count) {
   // staging tiles (17 KB) and the post-loop merge buffer (32 KB) share the same storage
   __shared__ __align__(16) unsigned char smraw[AM_TT * 16 * AM_TOP * sizeof(Cand)];
   __shared__ int short_list[AM_TT][AM_TOP];
@@ -98,7 +102,10 @@ l2_argmin_kernel(const float* __restrict__ z, int T, int E, const float* __restr
   static_assert(2 * AM_KC * AM_LD * sizeof(float) <= sizeof(smraw), "staging tiles must fit the merge buffer");
   const int tx = threadIdx.x & 15;          // code micro-column
   const int ty = threadIdx.x >> 4;          // token micro-row
-  const int t0 = blockIdx.x * AM_TT;
+  const int n_tok = list != nullptr ? *count : T;
+  for (int t0 = blockIdx.x * AM_TT; t0 < n_tok; t0 += gridDim.x * AM_TT) {
+  auto token = [&](int i) { return list != nullptr ? list[i] : i; };
+  __syncthreads();                          // the previous chunk's merge buffer / shortlist are no longer read
   Cand top[4][AM_TOP];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -115,10 +122,10 @@ l2_argmin_kernel(const float* __restrict__ z, int T, int E, const float* __restr
       for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
     for (int k0 = 0; k0 < E; k0 += AM_KC) {
       {
-        const int t = t0 + lrow;
+        const int ti = t0 + lrow;
         float4 a = make_float4(0, 0, 0, 0), b = a;
-        if (t < T) {
-          const float4* p = reinterpret_cast<const float4*>(z + (size_t)t * E + k0 + lcol);
+        if (ti < n_tok) {
+          const float4* p = reinterpret_cast<const float4*>(z + (size_t)token(ti) * E + k0 + lcol);
           a = __ldg(p); b = __ldg(p + 1);
         }
         xs[lcol + 0][lrow] = a.x; xs[lcol + 1][lrow] = a.y; xs[lcol + 2][lrow] = a.z; xs[lcol + 3][lrow] = a.w;
@@ -177,8 +184,8 @@ l2_argmin_kernel(const float* __restrict__ z, int T, int E, const float* __restr
   // fp64 re-evaluation of the shortlisted codes: one warp per token
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int tt = warp; tt < AM_TT; tt += 8) {
-    const int t = t0 + tt;
-    if (t >= T) continue;
+    if (t0 + tt >= n_tok) continue;
+    const int t = token(t0 + tt);
     double bd = 0.0;
     int bi = -1;
     for (int k = 0; k < AM_TOP; ++k) {
@@ -197,6 +204,15 @@ l2_argmin_kernel(const float* __restrict__ z, int T, int E, const float* __restr
     if (quant != nullptr)
       for (int e = lane; e < E; e += 32) quant[(size_t)t * E + e] = cb[(size_t)bi * E + e];
   }
+  }
+}
+
+int l2_argmin_list_launch(const float* z, int T, int E, const float* codebook, int K, int64_t* idx, float* quant,
+                          const int* list, const int* count, int grid, cudaStream_t st) {
+  if (E % AM_KC != 0) return PGT_ERR_UNSUPPORTED;
+  l2_argmin_kernel<<<grid, 256, 0, st>>>(z, T, E, codebook, K, idx, quant, list, count);
+  PGT_LAUNCH_OK();
+  return PGT_OK;
 }
 
 }  // namespace pgt
@@ -223,7 +239,7 @@ extern "C" int pgt_l2_argmin(const float* z, int T, int E, const float* codebook
   PGT_CHECK_ARG(z && codebook && idx && T > 0 && K > 0 && E > 0 && E % AM_KC == 0);
   PGT_CHECK_ARG((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(codebook) & 15) == 0);
   ProfScope ps(PGT_PROF_ARGMIN, 2.0 * T * (double)K * E, static_cast<cudaStream_t>(stream));
-  l2_argmin_kernel<<<ceil_div(T, AM_TT), 256, 0, static_cast<cudaStream_t>(stream)>>>(z, T, E, codebook, K, idx, quant);
+  l2_argmin_kernel<<<ceil_div(T, AM_TT), 256, 0, static_cast<cudaStream_t>(stream)>>>(z, T, E, codebook, K, idx, quant, nullptr, nullptr);
   PGT_LAUNCH_OK();
   return PGT_OK;
 }

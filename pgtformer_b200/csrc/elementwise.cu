@@ -3,6 +3,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "tmap.cuh"
 
 namespace pgt {
 
@@ -197,13 +198,12 @@ __global__ void gather_frames_kernel(const uint4* __restrict__ x, size_t vec_per
 
 extern "C" int pgt_u8hwc_to_f32nchw(const void* x_u8, int F, int H, int W, float* y, void* stream) {
   PGT_CHECK_ARG(x_u8 && y && F > 0 && H > 0 && W > 0);
-  static bool table = false;
-  if (!table) {
+  static pgt::PerDeviceOnce once;               // __constant__ memory is per device
+  PGT_CUDA_OK(once.run([] {
     float t[256];
     for (int v = 0; v < 256; ++v) t[v] = (float)((double)v / 255.0);
-    PGT_CUDA_OK(cudaMemcpyToSymbol(pgt::c_u8_to_unit, t, sizeof(t)));
-    table = true;
-  }
+    return cudaMemcpyToSymbol(pgt::c_u8_to_unit, t, sizeof(t));
+  }));
   const size_t HW = (size_t)H * W, total = (size_t)F * HW;
   ProfScope ps(PGT_PROF_MOVE, 15.0 * (double)total, static_cast<cudaStream_t>(stream), "pgt_u8hwc_to_f32nchw");
   pgt::u8hwc_to_f32nchw_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(

@@ -30,6 +30,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "tmap.cuh"
 #include "ptx.cuh"
 #include "epi_common.cuh"
 
@@ -1170,39 +1171,9 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------- host side
-static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess) {
-      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
-    }
-  }
-  return fn;
-}
-
 static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, int dtype = PGT_BF16) {
-  auto fn = get_encode_fn();
-  if (fn == nullptr) return PGT_ERR_DRIVER;
-  cuuint64_t gdim[5];
-  cuuint64_t gstr[4];
-  cuuint32_t bdim[5];
-  cuuint32_t estr[5];
-  for (int i = 0; i < rank; ++i) {
-    gdim[i] = dims[i];
-    bdim[i] = box[i];
-    estr[i] = 1;
-    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
-  }
-  CUresult r = fn(map, dtype == PGT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank,
-                  const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? PGT_OK : PGT_ERR_DRIVER;
+  return tmap_encode(map, base, rank, dims, strides_bytes, box, dtype);     // cached (tmap.cuh)
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -1286,11 +1257,8 @@ static int launch_gemm(const CUtensorMap& tmA, const void* W, int ldw, GemmParam
   if (rc != PGT_OK) return rc;
   p.n_tiles = ceil_div(p.N, BN);
   p.pair_map = PAIR ? 1 : 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PGT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  static PerDeviceOnce once;
+  PGT_CUDA_OK(once.run([] { return cudaFuncSetAttribute(gemm_tc_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); }));
   const int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (PAIR) grid &= ~1;
@@ -1327,11 +1295,8 @@ static int launch_halo(const CUtensorMap& tmA, const void* W, int ldw, GemmParam
   if (rc != PGT_OK) return rc;
   p.n_tiles = ceil_div(p.N, BN);
   p.b_resident = (p.ntaps * p.cin_blocks <= Cfg::B_STAGES && p.n_tiles == 1) ? 1 : 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PGT_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<BN, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  static PerDeviceOnce once;
+  PGT_CUDA_OK(once.run([] { return cudaFuncSetAttribute(conv_halo_kernel<BN, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); }));
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   {
@@ -1357,11 +1322,8 @@ static int launch_halo2(const CUtensorMap& tmA, const void* W, int ldw, GemmPara
   if (rc != PGT_OK) return rc;
   p.n_tiles = 1;
   p.b_resident = (p.ntaps * p.cin_blocks <= Cfg::B_STAGES) ? 1 : 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PGT_CUDA_OK(cudaFuncSetAttribute(conv_halo2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  static PerDeviceOnce once;
+  PGT_CUDA_OK(once.run([] { return cudaFuncSetAttribute(conv_halo2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); }));
   int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
   grid &= ~1;                                                            // whole CTA pairs
   {

@@ -16,6 +16,7 @@
 #include <cstdio>
 
 #include "common.cuh"
+#include "tmap.cuh"
 #include "ptx.cuh"
 
 namespace pgt {
@@ -284,23 +285,7 @@ ln_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 }
 
 static int ll_enc2d(CUtensorMap* map, const void* base, int ld, long long rows, int cols, int box_rows) {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-  if (fn == nullptr) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-      return PGT_ERR_DRIVER;
-    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
-  }
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? PGT_OK : PGT_ERR_DRIVER;
+  return tmap_rows_bf16(map, base, ld, rows, cols, box_rows);
 }
 
 }  // namespace pgt
@@ -318,11 +303,8 @@ extern "C" int pgt_ln_linear_bf16(const void* x, int ldx, int T, int C, const fl
   if (rc == PGT_OK) rc = ll_enc2d(&to, out, ldo, T, N, LL_BM);
   if (rc == PGT_OK) rc = ll_enc2d(&tw, W, ldw, N, C, LL_C);
   if (rc != PGT_OK) return rc;
-  static bool attr = false;
-  if (!attr) {
-    PGT_CUDA_OK(cudaFuncSetAttribute(ln_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LL_SMEM));
-    attr = true;
-  }
+  static PerDeviceOnce once;
+  PGT_CUDA_OK(once.run([] { return cudaFuncSetAttribute(ln_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LL_SMEM); }));
   LnLinearParams p{};
   p.T = T; p.m_tiles = ceil_div(T, LL_BM); p.nb = N / LL_C;
   p.ln_g = ln_g; p.ln_b = ln_b; p.eps = eps; p.bias = bias;

@@ -11,6 +11,7 @@
 #include <cudaTypedefs.h>
 
 #include "common.cuh"
+#include "tmap.cuh"
 #include "ptx.cuh"
 
 namespace pgt {
@@ -252,23 +253,7 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 }
 
 static int encode_rows_map(CUtensorMap* map, const void* base, int ld, long long rows, int cols) {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-  if (fn == nullptr) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-      return PGT_ERR_DRIVER;
-    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
-  }
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {FT_D, FT_BN};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? PGT_OK : PGT_ERR_DRIVER;
+  return tmap_rows_bf16(map, base, ld, rows, cols, FT_BN);
 }
 
 // Returns PGT_ERR_UNSUPPORTED when the shape is not covered (caller falls back to the mma.sync kernel).
@@ -283,11 +268,8 @@ int mha_tc_launch(const void* q, int ldq, const void* k, int ldk, const void* v,
   if (rc == PGT_OK) rc = encode_rows_map(&tk, k, ldk, rows, heads * d);
   if (rc == PGT_OK) rc = encode_rows_map(&tv, v, ldv, rows, heads * d);
   if (rc != PGT_OK) return rc;
-  static bool attr = false;
-  if (!attr) {
-    PGT_CUDA_OK(cudaFuncSetAttribute(mha_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
-    attr = true;
-  }
+  static PerDeviceOnce once;
+  PGT_CUDA_OK(once.run([] { return cudaFuncSetAttribute(mha_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM); }));
   dim3 grid(L / (2 * FT_BM), heads, clips);
   mha_tc_kernel<<<grid, FT_THREADS, FT_SMEM, stream>>>(tq, tk, tv, L, reinterpret_cast<__nv_bfloat16*>(out), ldo);
   PGT_LAUNCH_OK();

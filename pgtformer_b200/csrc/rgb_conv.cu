@@ -13,6 +13,7 @@
 #include <cudaTypedefs.h>
 
 #include "common.cuh"
+#include "tmap.cuh"
 #include "ptx.cuh"
 #include "epi_common.cuh"
 
@@ -212,37 +213,23 @@ rgb_conv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 }
 
 static int rc_enc2d(CUtensorMap* map, const void* base, long long ld, long long rows, int cols, int box_rows) {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-  if (fn == nullptr) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-      return PGT_ERR_DRIVER;
-    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
-  }
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? PGT_OK : PGT_ERR_DRIVER;
+  return tmap_rows_bf16(map, base, ld, rows, cols, box_rows);
 }
 
 template <int KS, int STRIDE, int PAD>
 static int launch_rgb(const CUtensorMap& tw, const CUtensorMap& to, const RgbConvParams& p, cudaStream_t st, const char* desc) {
   using Cfg = RgbCfg<KS>;
-  static bool attr = false;
-  static int per_sm = 1;
-  if (!attr) {
-    PGT_CUDA_OK(cudaFuncSetAttribute(rgb_conv_kernel<KS, STRIDE, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    PGT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rgb_conv_kernel<KS, STRIDE, PAD>, RC_THREADS, Cfg::SMEM));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;                 // 128 TMEM columns per CTA
-    attr = true;
-  }
+  static PerDeviceOnce once;
+  static int per_sm = 1;                        // identical on every device of the box (same chip)
+  PGT_CUDA_OK(once.run([] {
+    cudaError_t e = cudaFuncSetAttribute(rgb_conv_kernel<KS, STRIDE, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    int n = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rgb_conv_kernel<KS, STRIDE, PAD>, RC_THREADS, Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    per_sm = n < 1 ? 1 : (n > 4 ? 4 : n);       // 128 TMEM columns per CTA
+    return cudaSuccess;
+  }));
   const int grid = p.m_tiles < num_sms() * per_sm ? p.m_tiles : num_sms() * per_sm;
   {
     ProfScope ps(PGT_PROF_GEMM, 2.0 * (double)p.M * RC_N * Cfg::K, st, desc);

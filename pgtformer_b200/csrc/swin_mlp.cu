@@ -19,6 +19,7 @@
 #include <cudaTypedefs.h>
 
 #include "common.cuh"
+#include "tmap.cuh"
 #include "ptx.cuh"
 #include "epi_common.cuh"
 
@@ -303,23 +304,7 @@ swin_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 }
 
 static int enc2d(CUtensorMap* map, const void* base, int ld, long long rows, int cols, int box_rows) {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-  if (fn == nullptr) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-      return PGT_ERR_DRIVER;
-    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
-  }
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? PGT_OK : PGT_ERR_DRIVER;
+  return tmap_rows_bf16(map, base, ld, rows, cols, box_rows);
 }
 
 }  // namespace pgt
@@ -339,11 +324,8 @@ extern "C" int pgt_swin_mlp_bf16(const void* x, int ldx, int T, int C, const flo
   if (rc == PGT_OK) rc = enc2d(&t1, W1, C, C, C, SM_C);
   if (rc == PGT_OK) rc = enc2d(&t2, W2, C, C, C, SM_C);
   if (rc != PGT_OK) return rc;
-  static bool attr = false;
-  if (!attr) {
-    PGT_CUDA_OK(cudaFuncSetAttribute(swin_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM));
-    attr = true;
-  }
+  static PerDeviceOnce once;
+  PGT_CUDA_OK(once.run([] { return cudaFuncSetAttribute(swin_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM); }));
   SwinMlpParams p{};
   p.T = T; p.m_tiles = ceil_div(T, SM_BM);
   p.ln_g = ln_g; p.ln_b = ln_b; p.eps = eps; p.b1 = b1; p.b2 = b2; p.gn_stats = gn_stats;

@@ -104,6 +104,7 @@ class Engine:
                 heads = sd[name].shape[1]
                 idx = sd[p + '.relative_position_index'].view(-1).long()
                 w[p + '.bias_tab'] = sd[name].float()[idx].view(48, 48, heads).permute(2, 0, 1).contiguous()
+                w[p + '.tab16'] = ops.window_tables(w[p + '.bias_tab'])     # tcgen05 window kernel: bias + mask, 4 box layouts
                 w[p + '.qkv.weight'] = _pack_lin(torch.cat([sd[p + '.q.weight'], sd[p + '.kv.weight']], 0).float())
                 w[p + '.qkv.bias'] = torch.cat([sd[p + '.q.bias'], sd[p + '.kv.bias']], 0).float().contiguous()
         # global transformer: in_proj split into the (q,k) projection of LN(x)+pos and the v projection of LN(x)
@@ -119,6 +120,7 @@ class Engine:
     def _new(self, *shape, dtype=BF):
         return torch.empty(*shape, dtype=dtype, device=self.dev)
 
+    window_tc = True          # window attention core on TMA + tcgen05 (window_attn_tc.cu)
     fuse_ln_qkv = True        # norm1 + q/kv projection of the C=256 Swin blocks as one kernel
     fuse_swin_mlp = True      # LN + fc1 + GELU + fc2 + residual of the C=256 Swin blocks as one kernel
     # GroupNorm+SiLU applied inside the consuming 3x3 conv (pgt_conv_gn_bf16, bit-identical).  Off by default: the
@@ -194,7 +196,9 @@ class Engine:
         else:
             y = ops.layernorm(x, w[p + '.norm1.weight'], w[p + '.norm1.bias'], self._new(Fr, H, W, C))
             qkv = self._lin(y, p + '.attn.qkv', 3 * C)
-        a = ops.window_attention(qkv, Fr // 3, H, W, C, heads, shift, w[p + '.attn.bias_tab'], self._new(Fr, H, W, C))
+        a = self._new(Fr, H, W, C)
+        if not self.window_tc or ops.window_attention_tc(qkv, Fr // 3, H, W, C, heads, shift, w[p + '.attn.tab16'], a) is None:
+            ops.window_attention(qkv, Fr // 3, H, W, C, heads, shift, w[p + '.attn.bias_tab'], a)   # shapes the TMA kernel does not cover
         x = self._lin(a, p + '.attn.proj', C, residual=x)
         if C == 256 and self.fuse_swin_mlp:
             # norm2 + fc1 + GELU + fc2 + residual in one kernel (the hidden tile never leaves the SM)
@@ -572,7 +576,9 @@ class Engine:
         z_e = self._lin(h.view(T, -1), 'quant_conv', a.embed_dim, out_dtype=torch.float32)
         codes = torch.empty(T, dtype=torch.int64, device=self.dev)
         z_q = self._new(T, a.embed_dim, dtype=torch.float32)
-        ops.l2_argmin(z_e, self.w['codebook'], a.n_embed, codes, z_q)
+        if 'codebook.pack' not in self.w:                  # bf16 copy + norms for the tcgen05 argmin, once per load
+            self.w['codebook.pack'] = ops.codebook_pack(self.w['codebook'], a.n_embed)
+        ops.l2_argmin_tc(z_e, self.w['codebook'], self.w['codebook.pack'], a.n_embed, codes, z_q)
         loss = (z_e - z_q).pow(2).mean()
         codes = codes.view(Fr, hh, ww, 1)
         if code_only:

@@ -17,7 +17,10 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def _stream():
+def _stream(t=None):
+    """Current CUDA stream of the tensor's device (of the current device when no tensor is given)."""
+    if t is not None:
+        return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -238,6 +241,56 @@ def window_attention(qkv, clips, H, W, C, heads, shift, bias_tab, out):
     return out
 
 
+LOG2E = 1.4426950408889634
+
+
+def window_tables(bias):
+    """Bias / mask tables of pgt_window_attention_tc from the expanded relative-position bias [heads, 48, 48] fp32:
+    fp16 [4 types][heads][6][48][8] = (bias[pi(row)][pi(key)] - 100 * masked) * log2(e), where type 0 is an interior
+    window, 1 / 2 / 3 a window that wraps in x / y / both (last window column / row of a shifted block): the TMA boxes
+    of its halves land one after the other, which permutes the rows (pi), and the reference's {0, -100} shift mask
+    (`modules/rstt_layers.py:552-568`) separates tokens on different sides of the wrap."""
+    heads = bias.shape[0]
+    dev = bias.device
+    r = torch.arange(48, device=dev)
+    tabs = []
+    for t in range(4):
+        xs, ys = t & 1, (t >> 1) & 1
+        if t == 0:
+            f, iy, ix = r // 16, (r // 4) % 4, r % 4
+        elif t == 1:                                   # parts x in {W-2, W-1} then {0, 1}: rows [f][y][x(2)]
+            rr = r % 24
+            f, iy, ix = rr // 8, (rr % 8) // 2, rr % 2 + 2 * (r // 24)
+        elif t == 2:                                   # parts y in {H-2, H-1} then {0, 1}: rows [f][y(2)][x]
+            rr = r % 24
+            f, iy, ix = rr // 8, (rr % 8) // 4 + 2 * (r // 24), rr % 4
+        else:                                          # four quarter boxes, y outer / x inner: rows [f][y(2)][x(2)]
+            pp, rr = r // 12, r % 12
+            f, iy, ix = rr // 4, (rr % 4) // 2 + 2 * (pp // 2), rr % 2 + 2 * (pp % 2)
+        canon = f * 16 + iy * 4 + ix
+        b = bias[:, canon][:, :, canon].float()
+        lab = (iy >= 2).long() * 2 * ys + (ix >= 2).long() * xs
+        masked = (lab[:, None] != lab[None, :]).float() * -100.0
+        tt = (b + masked[None]) * LOG2E                                      # [heads, row, key]
+        tabs.append(tt.view(heads, 48, 6, 8).permute(0, 2, 1, 3))             # [heads, 6, row, 8]
+    return torch.stack(tabs, 0).to(torch.float16).contiguous()
+
+
+WINDOW_MODE_N64 = 0          # d = 32 heads: 0 = P V with a half-atom N = 32 view of V, 1 = N = 64 (both heads' columns)
+
+
+def window_attention_tc(qkv, clips, H, W, C, heads, shift, tab16, out, mode_n64=None):
+    """TMA + tcgen05 window attention core; returns None when the shape is not covered (caller uses window_attention)."""
+    lib = L.load()
+    assert qkv.dtype == torch.bfloat16 and tab16.dtype == torch.float16 and tab16.is_contiguous()
+    rc = lib.pgt_window_attention_tc(_p(qkv), _rows(qkv)[2], clips, H, W, C, heads, shift, _p(tab16), _p(out),
+                                     _rows(out)[2], WINDOW_MODE_N64 if mode_n64 is None else int(mode_n64), _stream(qkv))
+    if rc == -3:
+        return None
+    L.check(rc)
+    return out
+
+
 def mha(q, k, v, clips, L_, heads, d, out):
     lib = L.load()
     L.check(lib.pgt_mha_fwd(_p(q), _rows(q)[2], _p(k), _rows(k)[2], _p(v), _rows(v)[2], clips, L_, heads, d, _p(out),
@@ -261,6 +314,35 @@ def l2_argmin(z, codebook, K, idx_out, quant=None):
     T, E = z.shape
     assert z.dtype == torch.float32 and z.is_contiguous() and codebook.is_contiguous()
     L.check(lib.pgt_l2_argmin(_p(z), T, E, _p(codebook), K, _p(idx_out), _p(quant), _stream()))
+    return idx_out, quant
+
+
+def codebook_pack(codebook, K):
+    """Load-time pack for l2_argmin_tc: (bf16 copy [K, E], fp32 [K + 2] = ||e_k||^2, max||e~||^2, max||e - e~||^2)."""
+    lib = L.load()
+    E = codebook.shape[1]
+    assert codebook.dtype == torch.float32 and codebook.is_contiguous() and codebook.shape[0] >= K
+    cb16 = torch.empty(K, E, dtype=torch.bfloat16, device=codebook.device)
+    norm = torch.empty(K + 2, dtype=torch.float32, device=codebook.device)
+    L.check(lib.pgt_codebook_pack(_p(codebook), K, E, _p(cb16), _p(norm), _stream(codebook)))
+    return cb16, norm
+
+
+L2_ARGMIN_UNSUPPORTED = -3
+
+
+def l2_argmin_tc(z, codebook, pack, K, idx_out, quant=None):
+    """tcgen05 nearest-codebook argmin (exact, see l2_argmin_tc.cu); falls back to the exhaustive kernel for shapes the
+    tensor-core kernel does not cover (K % 256, E % 128, E > 512)."""
+    lib = L.load()
+    T, E = z.shape
+    assert z.dtype == torch.float32 and z.is_contiguous() and codebook.is_contiguous() and idx_out.dtype == torch.int64
+    ws = torch.empty(int(lib.pgt_l2_argmin_ws_ints(T)), dtype=torch.int32, device=z.device)
+    rc = lib.pgt_l2_argmin_tc(_p(z), T, E, _p(codebook), _p(pack[0]), _p(pack[1]), K, _p(idx_out), _p(quant), _p(ws),
+                              _stream(z))
+    if rc == L2_ARGMIN_UNSUPPORTED:
+        return l2_argmin(z, codebook, K, idx_out, quant)
+    L.check(rc)
     return idx_out, quant
 
 
