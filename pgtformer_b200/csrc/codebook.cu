@@ -1,7 +1,8 @@
-// RQ-VAE codebook kernels: row argmax + embedding gather (the path PGTFormer.forward takes) and the
-// nearest-codebook L2 argmin (the path TDCRQVAE3.forward / get_codes takes).  Index results are exact:
-// argmax is a pure fp32 compare; argmin is an fp32 shortlist (top-4 per token) re-evaluated in fp64, lowest
-// index on ties — it matches an fp64 argmin of ||z-e||^2, which is stricter than the reference's own fp32 addmm.
+// RQ-VAE codebook kernels: row argmax + embedding gather (the path PGTFormer.forward takes) and the exhaustive
+// fp64 nearest-codebook L2 argmin (the tcgen05 kernel of the TDCRQVAE3.forward / get_codes path is in
+// l2_argmin_tc.cu; this one serves the tokens it cannot certify and the shapes it does not cover).  Index results are
+// exact: argmax is a pure fp32 compare; argmin is an fp64 argmin of ||z-e||^2 with lowest index on ties, which is
+// stricter than the reference's own fp32 addmm.
 #include <float.h>
 
 #include "common.cuh"
@@ -63,147 +64,114 @@ argmax_gather_kernel(const float* __restrict__ logits, int T, int K, const float
   }
 }
 
-// ------------------------------------------------------------------------------ L2 argmin
+// ------------------------------------------------------------------------------ L2 argmin (exhaustive, fp64)
+// Every ||z - e_k||^2 is accumulated directly in fp64 (the differences of fp32 values are exact in fp64), running
+// (min, first index) per token: this IS the fp64 argmin the tests adjudicate against, for any scale of z and e
+// (an fp32 shortlist is not: with ||z|| >> ||e|| all 1024 distances agree to ~1e-6 relative, below fp32 resolution).
+// 64 tokens x 64 codes per tile, 4 x 4 fp64 accumulators per thread, two fp64 instructions per term (~3 ms at
+// T = 49152, K = 1024, E = 512 on the 64-lane fp64 pipe).  Runs on all T tokens (list == nullptr) for shapes the
+// tcgen05 kernel does not cover, or on the tokens list[0 .. *count) it could not certify — normally none.
 constexpr int AM_TT = 64;      // tokens per CTA
 constexpr int AM_TC = 64;      // codes per tile
 constexpr int AM_KC = 32;      // feature chunk
 constexpr int AM_LD = AM_TT + 4;
-constexpr int AM_TOP = 4;
 
-struct Cand {
-  float v;
+struct CandD {
+  double v;
   int i;
 };
-__device__ __forceinline__ bool cand_less(float v, int i, const Cand& c) { return v < c.v || (v == c.v && i < c.i); }
-__device__ __forceinline__ void cand_insert(Cand (&top)[AM_TOP], float v, int i) {
-  if (!cand_less(v, i, top[AM_TOP - 1])) return;
-  top[AM_TOP - 1].v = v; top[AM_TOP - 1].i = i;
-#pragma unroll
-  for (int k = AM_TOP - 1; k > 0; --k) {
-    if (cand_less(top[k].v, top[k].i, top[k - 1])) {
-      const Cand t = top[k]; top[k] = top[k - 1]; top[k - 1] = t;
-    }
-  }
-}
 
-// Exhaustive and exact: every code is scored in fp32 (direct sum of squared differences), the per-token top-4 is
-// re-evaluated in fp64.  Runs on all T tokens (list == nullptr), or on the tokens `list[0 .. *count)` that the
-// tcgen05 kernel (l2_argmin_tc.cu) could not certify — normally none, then every CTA returns at once.
 __global__ void __launch_bounds__(256)
 l2_argmin_kernel(const float* __restrict__ z, int T, int E, const float* __restrict__ cb, int K,
                  int64_t* __restrict__ idx, float* __restrict__ quant, const int* __restrict__ list,
                  const int* __restrict__ count) {
-  // staging tiles (17 KB) and the post-loop merge buffer (32 KB) share the same storage
-  __shared__ __align__(16) unsigned char smraw[AM_TT * 16 * AM_TOP * sizeof(Cand)];
-  __shared__ int short_list[AM_TT][AM_TOP];
-  float (*xs)[AM_LD] = reinterpret_cast<float (*)[AM_LD]>(smraw);
-  float (*es)[AM_LD] = reinterpret_cast<float (*)[AM_LD]>(smraw + AM_KC * AM_LD * sizeof(float));
-  Cand (*merge)[16][AM_TOP] = reinterpret_cast<Cand (*)[16][AM_TOP]>(smraw);
-  static_assert(2 * AM_KC * AM_LD * sizeof(float) <= sizeof(smraw), "staging tiles must fit the merge buffer");
+  __shared__ __align__(16) float xs[AM_KC][AM_LD];
+  __shared__ __align__(16) float es[AM_KC][AM_LD];
+  __shared__ CandD merge[AM_TT][16];
+  __shared__ int winner[AM_TT];
   const int tx = threadIdx.x & 15;          // code micro-column
   const int ty = threadIdx.x >> 4;          // token micro-row
   const int n_tok = list != nullptr ? *count : T;
-  for (int t0 = blockIdx.x * AM_TT; t0 < n_tok; t0 += gridDim.x * AM_TT) {
   auto token = [&](int i) { return list != nullptr ? list[i] : i; };
-  __syncthreads();                          // the previous chunk's merge buffer / shortlist are no longer read
-  Cand top[4][AM_TOP];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int k = 0; k < AM_TOP; ++k) { top[a][k].v = FLT_MAX; top[a][k].i = 0x7fffffff; }
-
   const int lrow = threadIdx.x >> 2;        // 0..63: token / code row this thread stages
   const int lcol = (threadIdx.x & 3) * 8;   // 8 consecutive features
-  for (int c0 = 0; c0 < K; c0 += AM_TC) {
-    float acc[4][4];
+  for (int t0 = blockIdx.x * AM_TT; t0 < n_tok; t0 += gridDim.x * AM_TT) {
+    CandD best[4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 4; ++a) { best[a].v = DBL_MAX; best[a].i = 0x7fffffff; }
+    for (int c0 = 0; c0 < K; c0 += AM_TC) {
+      double acc[4][4];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-    for (int k0 = 0; k0 < E; k0 += AM_KC) {
-      {
-        const int ti = t0 + lrow;
-        float4 a = make_float4(0, 0, 0, 0), b = a;
-        if (ti < n_tok) {
-          const float4* p = reinterpret_cast<const float4*>(z + (size_t)token(ti) * E + k0 + lcol);
-          a = __ldg(p); b = __ldg(p + 1);
-        }
-        xs[lcol + 0][lrow] = a.x; xs[lcol + 1][lrow] = a.y; xs[lcol + 2][lrow] = a.z; xs[lcol + 3][lrow] = a.w;
-        xs[lcol + 4][lrow] = b.x; xs[lcol + 5][lrow] = b.y; xs[lcol + 6][lrow] = b.z; xs[lcol + 7][lrow] = b.w;
-        const int c = c0 + lrow;
-        a = make_float4(0, 0, 0, 0); b = a;
-        if (c < K) {
-          const float4* p = reinterpret_cast<const float4*>(cb + (size_t)c * E + k0 + lcol);
-          a = __ldg(p); b = __ldg(p + 1);
-        }
-        es[lcol + 0][lrow] = a.x; es[lcol + 1][lrow] = a.y; es[lcol + 2][lrow] = a.z; es[lcol + 3][lrow] = a.w;
-        es[lcol + 4][lrow] = b.x; es[lcol + 5][lrow] = b.y; es[lcol + 6][lrow] = b.z; es[lcol + 7][lrow] = b.w;
-      }
-      __syncthreads();
-#pragma unroll 8
-      for (int k = 0; k < AM_KC; ++k) {
-        const float4 xv = *reinterpret_cast<const float4*>(&xs[k][ty * 4]);
-        const float4 ev = *reinterpret_cast<const float4*>(&es[k][tx * 4]);
-        const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
-        const float ea[4] = {ev.x, ev.y, ev.z, ev.w};
+      for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const float d = xa[a] - ea[b];
-            acc[a][b] = fmaf(d, d, acc[a][b]);
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+      for (int k0 = 0; k0 < E; k0 += AM_KC) {
+        {
+          const int ti = t0 + lrow;
+          float4 a = make_float4(0, 0, 0, 0), b = a;
+          if (ti < n_tok) {
+            const float4* p = reinterpret_cast<const float4*>(z + (size_t)token(ti) * E + k0 + lcol);
+            a = __ldg(p); b = __ldg(p + 1);
           }
+          xs[lcol + 0][lrow] = a.x; xs[lcol + 1][lrow] = a.y; xs[lcol + 2][lrow] = a.z; xs[lcol + 3][lrow] = a.w;
+          xs[lcol + 4][lrow] = b.x; xs[lcol + 5][lrow] = b.y; xs[lcol + 6][lrow] = b.z; xs[lcol + 7][lrow] = b.w;
+          const int c = c0 + lrow;
+          a = make_float4(0, 0, 0, 0); b = a;
+          if (c < K) {
+            const float4* p = reinterpret_cast<const float4*>(cb + (size_t)c * E + k0 + lcol);
+            a = __ldg(p); b = __ldg(p + 1);
+          }
+          es[lcol + 0][lrow] = a.x; es[lcol + 1][lrow] = a.y; es[lcol + 2][lrow] = a.z; es[lcol + 3][lrow] = a.w;
+          es[lcol + 4][lrow] = b.x; es[lcol + 5][lrow] = b.y; es[lcol + 6][lrow] = b.z; es[lcol + 7][lrow] = b.w;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < AM_KC; ++k) {
+          const float4 xv = *reinterpret_cast<const float4*>(&xs[k][ty * 4]);
+          const float4 ev = *reinterpret_cast<const float4*>(&es[k][tx * 4]);
+          const double xa[4] = {(double)xv.x, (double)xv.y, (double)xv.z, (double)xv.w};
+          const double ea[4] = {(double)ev.x, (double)ev.y, (double)ev.z, (double)ev.w};
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const double d = xa[a] - ea[b];
+              acc[a][b] = fma(d, d, acc[a][b]);
+            }
+        }
+        __syncthreads();
       }
-      __syncthreads();
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int c = c0 + tx * 4 + b;                      // ascending within the thread: strict < keeps the first
+          if (c < K && acc[a][b] < best[a].v) { best[a].v = acc[a][b]; best[a].i = c; }
+        }
     }
+    // merge the 16 per-thread minima of each token: lowest index on equal values
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int c = c0 + tx * 4 + b;
-        if (c < K) cand_insert(top[a], acc[a][b], c);
+    for (int a = 0; a < 4; ++a) merge[ty * 4 + a][tx] = best[a];
+    __syncthreads();
+    if (threadIdx.x < AM_TT) {
+      CandD w = merge[threadIdx.x][0];
+      for (int j = 1; j < 16; ++j) {
+        const CandD c = merge[threadIdx.x][j];
+        if (c.v < w.v || (c.v == w.v && c.i < w.i)) w = c;
       }
-  }
-  // merge the 16 per-thread shortlists of each token
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int k = 0; k < AM_TOP; ++k) merge[ty * 4 + a][tx][k] = top[a][k];
-  __syncthreads();
-  if (threadIdx.x < AM_TT) {
-    Cand best[AM_TOP];
-#pragma unroll
-    for (int k = 0; k < AM_TOP; ++k) { best[k].v = FLT_MAX; best[k].i = 0x7fffffff; }
-    for (int j = 0; j < 16; ++j)
-#pragma unroll
-      for (int k = 0; k < AM_TOP; ++k) cand_insert(best, merge[threadIdx.x][j][k].v, merge[threadIdx.x][j][k].i);
-#pragma unroll
-    for (int k = 0; k < AM_TOP; ++k) short_list[threadIdx.x][k] = best[k].i;
-  }
-  __syncthreads();
-  // fp64 re-evaluation of the shortlisted codes: one warp per token
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int tt = warp; tt < AM_TT; tt += 8) {
-    if (t0 + tt >= n_tok) continue;
-    const int t = token(t0 + tt);
-    double bd = 0.0;
-    int bi = -1;
-    for (int k = 0; k < AM_TOP; ++k) {
-      const int c = short_list[tt][k];
-      if (c < 0 || c >= K) continue;
-      double s = 0.0;
-      for (int e = lane; e < E; e += 32) {
-        const double d = (double)z[(size_t)t * E + e] - (double)cb[(size_t)c * E + e];
-        s += d * d;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (bi < 0 || s < bd || (s == bd && c < bi)) { bd = s; bi = c; }
+      winner[threadIdx.x] = w.i;
+      if (t0 + threadIdx.x < n_tok) idx[token(t0 + threadIdx.x)] = w.i;
     }
-    if (lane == 0) idx[t] = bi;
-    if (quant != nullptr)
-      for (int e = lane; e < E; e += 32) quant[(size_t)t * E + e] = cb[(size_t)bi * E + e];
-  }
+    __syncthreads();
+    if (quant != nullptr) {
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      for (int tt = warp; tt < AM_TT; tt += 8) {
+        if (t0 + tt >= n_tok) continue;
+        const int t = token(t0 + tt), bi = winner[tt];
+        for (int e = lane; e < E; e += 32) quant[(size_t)t * E + e] = cb[(size_t)bi * E + e];
+      }
+    }
+    __syncthreads();
   }
 }
 

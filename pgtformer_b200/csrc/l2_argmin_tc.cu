@@ -10,9 +10,10 @@
 //   * warp 0 streams the bf16 codebook (N-tile = 256 codes, k-block = 64) through a TMA ring, warp 1 issues
 //     tcgen05.mma 128x256x16 into a double-buffered 128 x 256 fp32 accumulator in TMEM;
 //   * the two epilogue warpgroups alternate N-tiles: thread = token row, d~_k = ||e_k||^2 - 2 s~ for its 256 codes,
-//     running minimum in a register; every code with d~_k <= running min + W is appended to the row's candidate list
-//     (a superset of the final window {k : d~_k <= min d~ + W}; ~ln K appends per row, so the scan stays 3-4
-//     instructions per code and warp divergence is rare).
+//     running minimum in a register; every code with d~_k <= running min + W is appended to the row's candidate list,
+//     which is emptied whenever the minimum drops by more than W (a superset of the final window
+//     {k : d~_k <= min d~ + W}; ~ln K appends per row, so the scan stays 3-4 instructions per code, warp divergence is
+//     rare and the list holds a handful of entries).
 // Certificate: |d~_k - d_k| <= D := 2 (||z - z~|| max||e~|| + ||z|| max||e - e~||) + slack (Cauchy-Schwarz on the two
 //   rounding-error dot products + fp32 accumulation slack), hence the true argmin lies in {k : d~_k <= min d~ + 2D},
 //   W = 2D.  The window's members (usually ONE) are re-evaluated exactly — fp32 direct sums, whose relative error is
@@ -39,6 +40,12 @@ constexpr int LT_THREADS = 64 + 256;
 constexpr int LT_TOP = 8;                        // window members resolved in-kernel (more -> exhaustive kernel)
 constexpr int LT_LIST = 16;                      // candidate-list capacity per (token, warpgroup)
 constexpr int LT_SMEM = LT_BM * LT_EMAX * 2 + LT_NST * LT_B_STAGE + 1280 /*barriers, z norms*/ + 1024 /*align*/;
+
+__device__ __forceinline__ float4 ld_nc_f4(const float4* p) {       // streaming 128-bit load (read once, keep out of L1)
+  float4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 
 // ------------------------------------------------------------------------------ codebook pack (load time)
 // bf16 copy of the codebook, ||e_k||^2 (fp64 sum rounded to fp32) and the two maxima the certificate needs:
@@ -163,37 +170,53 @@ l2_argmin_tc_kernel(const __grid_constant__ CUtensorMap tmB, const float* __rest
     // ---------------------------------------------------------------- 8 worker warps
     const int w8 = warp - 2;                                   // 0..7
     // (1) z rows -> bf16 A tile.  Warp w8 converts rows w8, w8+8, ...; a lane covers 8 consecutive floats per
-    //     256-float step (two 128-bit loads), i.e. exactly one 16-byte chunk of the swizzled row.
-    for (int r = w8; r < LT_BM; r += 8) {
-      const int t = t0 + r;
-      float s2 = 0.f, d2 = 0.f;
-      for (int c0 = 0; c0 < E; c0 += 256) {
-        const int c = c0 + lane * 8;
-        uint4 packed = make_uint4(0, 0, 0, 0);
-        if (t < T && c < E) {
-          float4 a, b;
-          const float* p = z + (size_t)t * E + c;
-          asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p));
-          asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p + 4));
-          const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-          uint32_t u[4];
+    //     256-float step (two 128-bit loads), i.e. exactly one 16-byte chunk of the swizzled row.  Four rows are
+    //     loaded before any is converted: 16 independent 128-bit loads in flight per lane.
+    constexpr int RB = 4;
+    const int nstep = (E + 255) / 256;                         // 1 or 2
+    for (int rb = w8; rb < LT_BM; rb += 8 * RB) {
+      float4 va[RB][2][2];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            u[q] = pack_bf16x2(f[2 * q], f[2 * q + 1]);
-            const float2 back = unpack_bf16x2(u[q]);
-            s2 = fmaf(f[2 * q], f[2 * q], s2); s2 = fmaf(f[2 * q + 1], f[2 * q + 1], s2);
-            const float e0 = f[2 * q] - back.x, e1 = f[2 * q + 1] - back.y;      // exact in fp32
-            d2 = fmaf(e0, e0, d2); d2 = fmaf(e1, e1, d2);
+      for (int i = 0; i < RB; ++i) {
+        const int t = t0 + rb + 8 * i;
+#pragma unroll
+        for (int sp = 0; sp < 2; ++sp) {
+          const int c = sp * 256 + lane * 8;
+          if (sp < nstep && t < T && c < E) {
+            const float4* p = reinterpret_cast<const float4*>(z + (size_t)t * E + c);
+            va[i][sp][0] = ld_nc_f4(p);
+            va[i][sp][1] = ld_nc_f4(p + 1);
+          } else {
+            va[i][sp][0] = va[i][sp][1] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          packed = make_uint4(u[0], u[1], u[2], u[3]);
-        }
-        if (c < E) {
-          const int kb = c >> 6, chunk = (c & 63) >> 3;
-          *reinterpret_cast<uint4*>(sA + kb * LT_A_KB_BYTES + r * 128 + ((chunk ^ (r & 7)) << 4)) = packed;
         }
       }
-      s2 = warp_sum(s2); d2 = warp_sum(d2);
-      if (lane == 0) { zn[r] = s2; dzn[r] = d2; }
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const int r = rb + 8 * i;
+        float s2 = 0.f, d2 = 0.f;
+#pragma unroll
+        for (int sp = 0; sp < 2; ++sp) {
+          const int c = sp * 256 + lane * 8;
+          if (sp < nstep && c < E) {
+            const float4 a = va[i][sp][0], b = va[i][sp][1];
+            const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            uint32_t u[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              u[q] = pack_bf16x2(f[2 * q], f[2 * q + 1]);
+              const float2 back = unpack_bf16x2(u[q]);
+              s2 = fmaf(f[2 * q], f[2 * q], s2); s2 = fmaf(f[2 * q + 1], f[2 * q + 1], s2);
+              const float e0 = f[2 * q] - back.x, e1 = f[2 * q + 1] - back.y;      // exact in fp32
+              d2 = fmaf(e0, e0, d2); d2 = fmaf(e1, e1, d2);
+            }
+            const int kb = c >> 6, chunk = (c & 63) >> 3;
+            *reinterpret_cast<uint4*>(sA + kb * LT_A_KB_BYTES + r * 128 + ((chunk ^ (r & 7)) << 4)) = make_uint4(u[0], u[1], u[2], u[3]);
+          }
+        }
+        s2 = warp_sum(s2); d2 = warp_sum(d2);
+        if (lane == 0) { zn[r] = s2; dzn[r] = d2; }
+      }
     }
     fence_proxy_async();                                       // generic-proxy writes of A -> visible to tcgen05.mma
     mbar_arrive(a_full);
@@ -234,9 +257,12 @@ l2_argmin_tc_kernel(const __grid_constant__ CUtensorMap tmB, const float* __rest
         for (int i = 0; i < 32; ++i) {
           const float d = fmaf(-2.f, __uint_as_float(v[i]), nv[i]);
           if (d <= thr) {
+            if (d < runmin) {
+              if (d + W < runmin) cnt = 0;                     // every earlier entry is now outside any final window
+              runmin = d; thr = d + W;
+            }
             if (cnt < LT_LIST && live) mylist[cnt] = make_float2(d, __int_as_float(nt * LT_BN + c + i));
             ++cnt;
-            if (d < runmin) { runmin = d; thr = d + W; }
           }
         }
       }

@@ -329,6 +329,12 @@ def codebook_pack(codebook, K):
 
 
 L2_ARGMIN_UNSUPPORTED = -3
+_last_argmin_ws = None
+
+
+def last_l2_argmin_fallbacks():
+    """Tokens of the last l2_argmin_tc call that went through the exhaustive kernel (diagnostics; synchronises)."""
+    return int(_last_argmin_ws[0].item()) if _last_argmin_ws is not None else 0
 
 
 def l2_argmin_tc(z, codebook, pack, K, idx_out, quant=None):
@@ -337,7 +343,9 @@ def l2_argmin_tc(z, codebook, pack, K, idx_out, quant=None):
     lib = L.load()
     T, E = z.shape
     assert z.dtype == torch.float32 and z.is_contiguous() and codebook.is_contiguous() and idx_out.dtype == torch.int64
+    global _last_argmin_ws
     ws = torch.empty(int(lib.pgt_l2_argmin_ws_ints(T)), dtype=torch.int32, device=z.device)
+    _last_argmin_ws = ws
     rc = lib.pgt_l2_argmin_tc(_p(z), T, E, _p(codebook), _p(pack[0]), _p(pack[1]), K, _p(idx_out), _p(quant), _p(ws),
                               _stream(z))
     if rc == L2_ARGMIN_UNSUPPORTED:

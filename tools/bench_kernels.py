@@ -91,13 +91,20 @@ def bench_argmin(T, regime, pk, out, with_ffma=True):
     cases = [('tcgen05', lambda: ops.l2_argmin_tc(z, cb, pack, 1024, idx, None)),
              ('tcgen05+quant', lambda: ops.l2_argmin_tc(z, cb, pack, 1024, idx, quant))]
     if with_ffma:
-        cases.append(('ffma', lambda: ops.l2_argmin(z, cb, 1024, idx, None)))
+        cases.append(('fp64_exhaustive', lambda: ops.l2_argmin(z, cb, 1024, idx, None)))
     for name, fn in cases:
-        ms = timed(fn, iters=5 if name == 'ffma' else 10)
-        fb = int(torch.zeros(1)[0])
-        out({'kernel': 'l2_argmin', 'impl': name, 'T': T, 'regime': regime, 'ms': ms, 'TFLOPs': flops / ms / 1e9,
-             'tensor_frac_burst': flops / ms / 1e9 / pk['bf16_tflops'], 'GBps': bytes_ / ms / 1e6,
-             'hbm_frac': bytes_ / ms / 1e6 / pk['hbm_gbs'], 'fallback_tokens': fb})
+        ms = timed(fn, iters=5 if name == 'fp64_exhaustive' else 10)
+        # device time of the sweep kernel alone (events around the launch inside the library)
+        ops.profile_begin()
+        for _ in range(5):
+            flush_l2()
+            fn()
+        prof = ops.profile_end()
+        kms = prof['l2_argmin'][1] / max(prof['l2_argmin'][2], 1)
+        out({'kernel': 'l2_argmin', 'impl': name, 'T': T, 'regime': regime, 'ms': ms, 'kernel_ms': kms,
+             'TFLOPs': flops / kms / 1e9, 'tensor_frac_burst': flops / kms / 1e9 / pk['bf16_tflops'],
+             'GBps': bytes_ / kms / 1e6, 'hbm_frac': bytes_ / kms / 1e6 / pk['hbm_gbs'],
+             'fallback_tokens': int(ops.last_l2_argmin_fallbacks())})
 
 
 def bench_argmax(T, pk, out):
