@@ -129,6 +129,84 @@ def cpu_oracle_clips_per_s(H, warmup, steps):
     return steps / dt, torch.get_num_threads()
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel class, from the committed ncu
+    capture of this command (profiles/r2_traffic.json, written by tools/summarize_profiles.py); None if absent."""
+    p = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+def parity_block(model, dev):
+    """Golden-vector parity of THIS process's model (same weights, same kernels as the timed steps): the reference's
+    own 512^2 outputs and its inference.py loop on the demo video (tools/parity_check.py; fixtures in tests/golden)."""
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    out = {}
+    try:
+        import parity_check as P
+        out['golden_512'] = P.check_compact(model, 512, dev)
+        out['demo_video_first8'] = P.check_demo_video(model)
+    except Exception as e:                                     # never lose the throughput line to the checker
+        out['error'] = repr(e)
+    return out
+
+
+def north_star_kernels(b, H, dev, peaks):
+    """Window attention (largest level of the workload) and the nearest-codebook L2 argmin at the workload's token
+    count, timed alone: achieved HBM GB/s and tensor TFLOP/s against the measured peaks (burst figures: kernels timed
+    in isolation)."""
+    import torch
+    from pgtformer_b200 import ops
+    from pgtformer_b200.weights import relative_position_index
+    res = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def run(fn, cls, iters=8):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ops.profile_begin()
+        for _ in range(iters):
+            flush.zero_()
+            fn()
+        pr = ops.profile_end()
+        return pr[cls][1] / max(pr[cls][2], 1)
+
+    try:
+        g = torch.Generator().manual_seed(5)
+        C, heads, hw = 256, 8, H // 4                           # decoder / encoder level 2: the largest attention level
+        T = b * 3 * hw * hw
+        qkv = torch.randn(T, 3 * C, generator=g).bfloat16().to(dev)
+        bias = (0.02 * torch.randn(245, heads, generator=g))[relative_position_index().view(-1)].view(48, 48, heads)
+        tab = ops.window_tables(bias.permute(2, 0, 1).contiguous().to(dev))
+        o = torch.empty(T, C, dtype=torch.bfloat16, device=dev)
+        ms = run(lambda: ops.window_attention_tc(qkv, b, hw, hw, C, heads, 2, tab, o), 'window_attn')
+        by = T * 4 * C * 2
+        res['window_attention'] = {'shape': '%d windows of 48 tokens, C=256, 8 heads, shifted' % (T // 48), 'kernel_ms': ms,
+                                   'algorithmic_bytes': by, 'achieved_hbm_gbs': by / ms / 1e6,
+                                   'hbm_frac': by / ms / 1e6 / peaks['hbm_gbs'],
+                                   'achieved_tflops': 4.0 * 48 * 48 * C * (T // 48) / ms / 1e9}
+        Tq = b * 3 * (H // 16) ** 2
+        cb = torch.randn(1025, 512, generator=g).to(dev)
+        z = torch.randn(Tq, 512, generator=g).to(dev)
+        idx = torch.empty(Tq, dtype=torch.int64, device=dev)
+        pack = ops.codebook_pack(cb, 1024)
+        ms = run(lambda: ops.l2_argmin_tc(z, cb, pack, 1024, idx, None), 'l2_argmin')
+        fl, by = 2.0 * Tq * 1024 * 512, Tq * 512 * 4 + 1024 * 512 * 4 + Tq * 8
+        res['l2_argmin'] = {'shape': 'T=%d tokens x 1024 codes x 512 (random z: the small-margin regime)' % Tq, 'kernel_ms': ms,
+                            'achieved_tflops': fl / ms / 1e9, 'tensor_frac': fl / ms / 1e9 / peaks['bf16_tflops'],
+                            'algorithmic_bytes': by, 'achieved_hbm_gbs': by / ms / 1e6,
+                            'hbm_frac': by / ms / 1e6 / peaks['hbm_gbs'],
+                            'exhaustive_fallback_tokens': ops.last_l2_argmin_fallbacks()}
+    except Exception as e:
+        res['error'] = repr(e)
+    return res
+
+
 def run_reference(args):
     """`--impl reference`: the reference's own CPU implementation of the path (oracle port), host cores only."""
     rank = int(os.environ.get('RANK', '0'))
@@ -158,6 +236,9 @@ def main():
     ap.add_argument('--size', type=int, default=512)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--graph', action='store_true', help='replay the forward from a CUDA graph')
+    ap.add_argument('--gather', default='middle_u8', choices=['middle_u8', 'full'],
+                    help='N > 1: what the end-of-step all-gather carries (restored middle frames as rgb24, or every fp32 frame)')
+    ap.add_argument('--no-parity', action='store_true', help='skip the golden-vector parity block of the JSON line')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -187,13 +268,17 @@ def main():
     x_host = torch.rand(b * 3, 3, H, H, generator=g).pin_memory()
     x_dev = x_host.to(dev)
     out_host = torch.empty(b * 3, 3, H, H, dtype=torch.float32).pin_memory()
-    from pgtformer_b200.parallel import gather_frames
+    from pgtformer_b200.parallel import gather_frames, gather_restored
+
+    def collective(out):
+        # the path's one collective, NCCL: the restored middle frames as rgb24 — what the consumer of the
+        # path keeps (inference.py:15-19) — or, with --gather full, every fp32 output frame
+        if world == 1:
+            return out
+        return gather_frames(out, world * b) if args.gather == 'full' else gather_restored(out, world * b)
 
     def step_resident():
-        out = model(x_dev, w=1, adain=True)[0]
-        if world > 1:
-            out = gather_frames(out, world * b)             # the path's one collective, NCCL
-        return out
+        return collective(model(x_dev, w=1, adain=True)[0])
 
     # end to end as a serving loop would run it: the pinned-host -> device copy of step k+1 and the device -> host copy
     # of step k's result ride their own streams and overlap the compute of the neighbouring step; every step still does
@@ -207,11 +292,12 @@ def main():
         main_stream.wait_stream(h2d_stream)
         xd.record_stream(main_stream)
         out = model(xd, w=1, adain=True)[0]
+        gathered = collective(out)                              # N > 1: the collective is part of the end-to-end step too
         d2h_stream.wait_stream(main_stream)
         with torch.cuda.stream(d2h_stream):
             out_host.copy_(out, non_blocking=True)
         out.record_stream(d2h_stream)
-        return out
+        return gathered
 
     def finish_e2e():
         main_stream.wait_stream(h2d_stream)
@@ -262,6 +348,13 @@ def main():
     prof = ops.profile_end()
     peaks, peak_kind = measured_peaks()
 
+    # the two north_star kernels that are not the dominant class, measured on their own at this workload's shapes
+    # (events around each launch inside the library; L2 flushed between launches)
+    ns_kernels = north_star_kernels(b, H, dev, peaks) if rank == 0 else None
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_block(model, dev)
+
     if rank == 0:
         work, pms, n = prof['gemm_tc']
         achieved = work / (pms / 1000.0) / 1e12 if pms > 0 else 0.0
@@ -290,7 +383,18 @@ def main():
                          'pass': 'separate profiled pass of the same %d steps' % args.steps,
                          'end_to_end_frac': value / world * flops_per_clip(H) / (peak * 1e12)},
             'kernel_breakdown': breakdown,
+            'north_star_kernels': ns_kernels,
+            'parity': parity,
         }
+        tr = load_traffic()
+        if tr is not None:
+            line['roofline']['traffic'] = tr.get('dram_bytes_per_launch')
+            line['roofline']['traffic_source'] = tr.get('source')
+            line['roofline']['algorithmic_bytes_per_launch'] = tr.get('algorithmic_bytes_per_launch')
+        if world > 1:
+            line['config']['collective'] = ('all_gather of the restored middle frames (rgb24, %d B/rank)' % (b * H * H * 3)
+                                            if args.gather == 'middle_u8' else
+                                            'all_gather of every fp32 output frame (%d B/rank)' % (b * 9 * H * H * 4))
         if world == 1 and not args.no_cpu_baseline:
             try:
                 v, cores = cpu_oracle_clips_per_s(H, 1, 1)

@@ -84,7 +84,7 @@ struct CandD {
 __global__ void __launch_bounds__(256)
 l2_argmin_kernel(const float* __restrict__ z, int T, int E, const float* __restrict__ cb, int K,
                  int64_t* __restrict__ idx, float* __restrict__ quant, const int* __restrict__ list,
-                 const int* __restrict__ count) {
+                 const int* __restrict__ count, int min_count) {
   __shared__ __align__(16) float xs[AM_KC][AM_LD];
   __shared__ __align__(16) float es[AM_KC][AM_LD];
   __shared__ CandD merge[AM_TT][16];
@@ -92,6 +92,7 @@ l2_argmin_kernel(const float* __restrict__ z, int T, int E, const float* __restr
   const int tx = threadIdx.x & 15;          // code micro-column
   const int ty = threadIdx.x >> 4;          // token micro-row
   const int n_tok = list != nullptr ? *count : T;
+  if (list != nullptr && n_tok <= min_count) return;      // short lists belong to l2_argmin_short_list_kernel
   auto token = [&](int i) { return list != nullptr ? list[i] : i; };
   const int lrow = threadIdx.x >> 2;        // 0..63: token / code row this thread stages
   const int lcol = (threadIdx.x & 3) * 8;   // 8 consecutive features
@@ -175,10 +176,52 @@ l2_argmin_kernel(const float* __restrict__ z, int T, int E, const float* __restr
   }
 }
 
+// The same fp64 argmin for a SHORT token list (the normal case of the tcgen05 kernel's leftovers: none, or a handful):
+// one warp per token, the codebook streamed from L2, so a few tokens spread over the whole chip instead of queueing on
+// one CTA of the tiled kernel.  Does nothing when *count > max_count (the tiled kernel takes over).
+__global__ void __launch_bounds__(256)
+l2_argmin_short_list_kernel(const float* __restrict__ z, int E, const float* __restrict__ cb, int K,
+                            int64_t* __restrict__ idx, float* __restrict__ quant, const int* __restrict__ list,
+                            const int* __restrict__ count, int max_count) {
+  const int n_tok = *count;
+  if (n_tok > max_count) return;
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int i = gw; i < n_tok; i += nw) {
+    const int t = list[i];
+    double bd = DBL_MAX;
+    int bi = 0x7fffffff;
+    for (int k = 0; k < K; ++k) {
+      double s = 0.0;
+      for (int e = lane * 4; e < E; e += 128) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(z + (size_t)t * E + e));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(cb + (size_t)k * E + e));
+        double d;
+        d = (double)a.x - (double)b.x; s = fma(d, d, s);
+        d = (double)a.y - (double)b.y; s = fma(d, d, s);
+        d = (double)a.z - (double)b.z; s = fma(d, d, s);
+        d = (double)a.w - (double)b.w; s = fma(d, d, s);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (s < bd) { bd = s; bi = k; }                          // ascending k: strict < keeps the first minimum
+    }
+    if (lane == 0) idx[t] = bi;
+    if (quant != nullptr)
+      for (int e = lane; e < E; e += 32) quant[(size_t)t * E + e] = cb[(size_t)bi * E + e];
+  }
+}
+
+constexpr int AM_SHORT_LIST = 2048;
+
 int l2_argmin_list_launch(const float* z, int T, int E, const float* codebook, int K, int64_t* idx, float* quant,
                           const int* list, const int* count, int grid, cudaStream_t st) {
-  if (E % AM_KC != 0) return PGT_ERR_UNSUPPORTED;
-  l2_argmin_kernel<<<grid, 256, 0, st>>>(z, T, E, codebook, K, idx, quant, list, count);
+  if (E % AM_KC != 0 || E % 4 != 0) return PGT_ERR_UNSUPPORTED;
+  // two launches that look at *count on the device: short lists one warp per token over the whole chip, long lists
+  // (degenerate codebooks) through the tiled kernel; with *count == 0 both return at once
+  l2_argmin_short_list_kernel<<<num_sms(), 256, 0, st>>>(z, E, codebook, K, idx, quant, list, count, AM_SHORT_LIST);
+  PGT_LAUNCH_OK();
+  l2_argmin_kernel<<<grid, 256, 0, st>>>(z, T, E, codebook, K, idx, quant, list, count, AM_SHORT_LIST);
   PGT_LAUNCH_OK();
   return PGT_OK;
 }
@@ -207,7 +250,7 @@ extern "C" int pgt_l2_argmin(const float* z, int T, int E, const float* codebook
   PGT_CHECK_ARG(z && codebook && idx && T > 0 && K > 0 && E > 0 && E % AM_KC == 0);
   PGT_CHECK_ARG((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(codebook) & 15) == 0);
   ProfScope ps(PGT_PROF_ARGMIN, 2.0 * T * (double)K * E, static_cast<cudaStream_t>(stream));
-  l2_argmin_kernel<<<ceil_div(T, AM_TT), 256, 0, static_cast<cudaStream_t>(stream)>>>(z, T, E, codebook, K, idx, quant, nullptr, nullptr);
+  l2_argmin_kernel<<<ceil_div(T, AM_TT), 256, 0, static_cast<cudaStream_t>(stream)>>>(z, T, E, codebook, K, idx, quant, nullptr, nullptr, 0);
   PGT_LAUNCH_OK();
   return PGT_OK;
 }

@@ -18,7 +18,7 @@
 //   rounding-error dot products + fp32 accumulation slack), hence the true argmin lies in {k : d~_k <= min d~ + 2D},
 //   W = 2D.  The window's members (usually ONE) are re-evaluated exactly — fp32 direct sums, whose relative error is
 //   bounded by 23 ulp, decide unless two candidates are closer than that bound, in which case fp64 decides (lowest
-//   index on ties).  Rows whose window holds more than 8 codes or whose list overflowed (degenerate codebooks: many
+//   index on ties).  Rows whose window holds more than 16 codes or whose list overflowed (degenerate codebooks: many
 //   duplicated / zero rows) are appended to a list for the exhaustive fp32+fp64 kernel in codebook.cu.
 // The result therefore equals an fp64 argmin of ||z - e_k||^2 with first-index tie-break for every input.
 #include <float.h>
@@ -37,7 +37,7 @@ constexpr int LT_EMAX = 512;                     // A tile resident: 128 x 512 b
 constexpr int LT_A_KB_BYTES = LT_BM * 128;       // 16 KB per k-block of A
 constexpr int LT_B_STAGE = LT_BN * 128;          // 32 KB
 constexpr int LT_THREADS = 64 + 256;
-constexpr int LT_TOP = 8;                        // window members resolved in-kernel (more -> exhaustive kernel)
+constexpr int LT_TOP = 16;                       // window members resolved in-kernel (more -> exhaustive kernel)
 constexpr int LT_LIST = 16;                      // candidate-list capacity per (token, warpgroup)
 constexpr int LT_SMEM = LT_BM * LT_EMAX * 2 + LT_NST * LT_B_STAGE + 1280 /*barriers, z norms*/ + 1024 /*align*/;
 
@@ -102,7 +102,7 @@ l2_argmin_tc_kernel(const __grid_constant__ CUtensorMap tmB, const float* __rest
   // after the sweep the codebook ring is dead: the warpgroups exchange their scan results through it
   float* xmin = reinterpret_cast<float*>(sB);                  // [2][128] running minima
   int* xcnt = reinterpret_cast<int*>(sB + 1024);               // [2][128] list lengths (> LT_LIST: overflowed)
-  int* mi = reinterpret_cast<int*>(sB + 2048);                 // [128][8] window members
+  int* mi = reinterpret_cast<int*>(sB + 2048);                 // [128][LT_TOP] window members
   int* ncand = reinterpret_cast<int*>(sB + 2048 + LT_BM * LT_TOP * 4);   // [128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -422,5 +422,5 @@ extern "C" int pgt_l2_argmin_tc(const float* z, int T, int E, const float* codeb
     PGT_LAUNCH_OK();
   }
   // tokens whose certificate window did not fit the shortlist (degenerate codebooks): exhaustive exact kernel
-  return l2_argmin_list_launch(z, T, E, codebook, K, idx, quant, workspace + 2, workspace, 64, st);
+  return l2_argmin_list_launch(z, T, E, codebook, K, idx, quant, workspace + 2, workspace, num_sms(), st);
 }

@@ -37,3 +37,17 @@ def gather_frames(local, n_clips, frames_per_clip=3):
     buf = local.new_empty((mx * world,) + tuple(local.shape[1:]))
     dist.all_gather_into_tensor(buf, pad)
     return torch.cat([buf[r * mx:r * mx + counts[r]] for r in range(world)], 0)
+
+
+def restored_middle_u8(out):
+    """What the consumer of the path keeps (`inference.py:15-19`): the middle frame of every clip as
+    uint8(clamp(x, 0, 1) * 255), rgb24 [clips, H, W, 3] — computed on the device (12x fewer bytes than fp32 `out`)."""
+    from . import ops
+    n = out.shape[0] // 3
+    return ops.f32nchw_to_u8hwc(out, torch.empty(n, out.shape[2], out.shape[3], 3, dtype=torch.uint8, device=out.device),
+                                first=1, step=3)
+
+
+def gather_restored(out, n_clips):
+    """The path's one collective in the form the consumer needs: all-gather of the restored middle frames (rgb24)."""
+    return gather_frames(restored_middle_u8(out), n_clips, frames_per_clip=1)

@@ -89,3 +89,25 @@ def test_oracle_matches_live_reference_when_present(network_g, arch_spec, synth_
         oo = O.pgtformer_forward(synth_sd, arch, x, 1.0, True)
     for a, b in zip(ro, oo):
         assert (a - b).abs().max() < TOL * 10
+
+
+def test_oracle_matches_full_size_reference_golden(arch_spec, synth_sd):
+    """512^2 is the unpatched reference's native size: the oracle restatement against the compact fixture minted from
+    it (every code index, sampled logit rows, lq_feat and the middle output frame stored as fp16)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    from oracle import pgt_oracle as O
+    from oracle.make_golden import golden_input as gi_oracle
+    from parity_check import golden_input, load_compact
+    g = load_compact(512)
+    x = golden_input(g['seed'], g['b'], g['H'])
+    assert torch.equal(x, gi_oracle(g['seed'], g['b'], g['H']))
+    arch, _ = arch_spec
+    with torch.no_grad():
+        out, logits, lq = O.pgtformer_forward(synth_sd, arch, x, 1.0, True)
+    lo = logits.reshape(-1, logits.shape[-1])
+    assert torch.equal(lo.argmax(-1), g['codes'].long().reshape(-1))
+    rows = g['logit_rows_idx'].long()
+    assert (lo[rows] - g['logit_rows']).abs().max().item() < 2e-5 * g['logits_absmax'] + 1e-5
+    assert (lq - g['lq_feat'].float()).abs().max().item() < 1.5e-3 * g['lq_absmax']          # fp16 storage of the fixture
+    assert (out[1::3] - g['out_mid'].float()).abs().max().item() < 1.5e-3 * g['out_absmax']
