@@ -104,6 +104,14 @@ int pgt_linear_bf16(const void* A, int lda, const void* W, int ldw, int M, int N
 int pgt_conv_bf16(const void* x, int F, int Hin, int Win, int Cin, int ldx, const void* Wp, int ldw,
                   int Cout, int ksize, int stride, int pad_lo, const pgt_epilogue* ep, void* stream);
 
+/* ---- decoder tail: GroupNorm(32) -> SiLU -> 3x3 conv to <= 3 channels -> fp32 NCHW, one tcgen05 kernel (conv_out.cu).
+ * x: RAW (pre-norm) bf16 [F, H, W, 64]; gn_ab: fp32 [F][2][64] from pgt_groupnorm_ab; Wp: packed [Cout, 9*64] bf16;
+ * out: fp32 [F, Cout, H, W].  Replaces norm_out / nonlinearity / conv_out at the end of the decoder
+ * (archs/pgtformer_arch.py:707-710, archs/tdcrqvae3_arch.py:700-706).  PGT_ERR_UNSUPPORTED unless Cin == 64,
+ * Cout <= 3, H % 16 == 0, W % 8 == 0. */
+int pgt_conv_out_gn(const void* x, int F, int H, int W, int Cin, int ldx, const float* gn_ab, const void* Wp, int ldw,
+                    int Cout, const float* bias, float* out, void* stream);
+
 /* ---- GroupNorm(32)+SiLU of the INPUT fused into the 3x3 / stride 1 / pad 1 conv: the normalised activation is never
  * written to HBM — the kernel applies y = silu(x * a[f,c] + b[f,c]) to each input slab in shared memory (bit-identical
  * to pgt_groupnorm_silu's apply pass) before the MMAs read it.  gn_ab: fp32 [F][2][Cin] from pgt_groupnorm_ab.

@@ -40,6 +40,8 @@ SIGNATURES = {
     'pgt_conv_gn_supported': (c_int, [c_int, c_int, c_int, c_int]),
     'pgt_conv_gn_bf16': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                  c_void_p]),
+    'pgt_conv_out_gn': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                c_void_p, c_void_p]),
     'pgt_groupnorm_ab': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int,
                                  c_void_p, c_void_p, c_void_p]),
     'pgt_conv_up2x_bf16': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,

@@ -120,6 +120,7 @@ class Engine:
     def _new(self, *shape, dtype=BF):
         return torch.empty(*shape, dtype=dtype, device=self.dev)
 
+    fuse_conv_out = True      # decoder norm_out + SiLU + conv_out (64 -> 3) as one kernel (conv_out.cu)
     window_tc = True          # window attention core on TMA + tcgen05 (window_attn_tc.cu)
     fuse_ln_qkv = True        # norm1 + q/kv projection of the C=256 Swin blocks as one kernel
     fuse_swin_mlp = True      # LN + fc1 + GELU + fc2 + residual of the C=256 Swin blocks as one kernel
@@ -453,6 +454,15 @@ class Engine:
                 h = ops.conv_up2x(h, self.w[p + '.weight'], C, out, bias=self.w[p + '.bias'], gn_stats=stats)
         Fr, H, W, _ = h.shape
         out = self._new(Fr, a.out_ch, H, W, dtype=torch.float32)
+        if self.fuse_conv_out:
+            # norm_out + SiLU + conv_out in one kernel: the normalised 512^2 tensor never reaches HBM
+            st = getattr(h, '_pgt_gn', None)
+            ab = ops.groupnorm_ab(h, self.w['decoder.norm_out.weight'], self.w['decoder.norm_out.bias'],
+                                  self._new(Fr * 2 * h.shape[-1], dtype=torch.float32),
+                                  stats=st[0] if st else None, chunks_per_frame=st[1] if st else 0)
+            if ops.conv_out_gn(h, ab, self.w['decoder.conv_out.weight'], a.out_ch, self.w.get('decoder.conv_out.bias'),
+                               out) is not None:
+                return out
         self._conv3(h, 'decoder.conv_out', a.out_ch, out=out, gn='decoder.norm_out', nchw=True)
         return out
 

@@ -187,6 +187,21 @@ def groupnorm_ab(x, gamma, beta, ab, stats=None, chunks_per_frame=0, eps=1e-6):
     return ab
 
 
+def conv_out_gn(x, ab, wp, cout, bias, out):
+    """conv3x3(silu(groupnorm(x))) -> fp32 NCHW for the decoder tail (Cin = 64, Cout <= 3); None when not covered."""
+    lib = L.load()
+    F, H, W, Cin = x.shape
+    assert x.dtype == torch.bfloat16 and x.stride(3) == 1 and x.stride(1) == W * x.stride(2) and \
+        (F == 1 or x.stride(0) == H * x.stride(1))
+    assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (F, cout, H, W)
+    rc = lib.pgt_conv_out_gn(_p(x), F, H, W, Cin, x.stride(2), _p(ab), _p(wp), wp.stride(0), cout, _p(bias), _p(out),
+                             _stream(x))
+    if rc == -3:
+        return None
+    L.check(rc)
+    return out
+
+
 def conv_gn_supported(H, W, cin, cout):
     return bool(L.load().pgt_conv_gn_supported(H, W, cin, cout))
 

@@ -197,3 +197,30 @@ def test_l2_argmin_tc_equals_exhaustive_kernel(synth_sd):
     o.l2_argmin(z, cb, 1024, a)
     o.l2_argmin_tc(z, cb, o.codebook_pack(cb, 1024), 1024, b)
     assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------ decoder tail
+@pytest.mark.parametrize('F,H,W', [(3, 32, 32), (2, 64, 48), (1, 16, 8)])
+def test_conv_out_gn_fused(F, H, W):
+    """norm_out -> SiLU -> conv_out (64 -> 3) as one kernel vs the oracle ops on the same bf16-rounded input / weights.
+    The kernel rounds the activated tensor to bf16 (MMA operand), as the separate GroupNorm pass did; the oracle side
+    emulates that rounding, so what remains is the approximate SiLU flipping an occasional bf16 ulp (3e-3 * max|ref|)."""
+    import torch.nn.functional as Fn
+    o = ops()
+    x = rnd((F, H, W, 64), 31, 1.5).bfloat16()
+    gamma, beta = 1.0 + 0.2 * rnd((64,), 32), 0.1 * rnd((64,), 33)
+    w = (0.05 * rnd((3, 64, 3, 3), 34))
+    bias = 0.1 * rnd((3,), 35)
+    wp = w.permute(0, 2, 3, 1).reshape(3, 9 * 64).bfloat16().contiguous()
+    xd = x.to(DEV)
+    ab = o.groupnorm_ab(xd, gamma.to(DEV), beta.to(DEV), torch.empty(F * 2 * 64, dtype=torch.float32, device=DEV))
+    out = torch.full((F, 3, H, W), float('nan'), dtype=torch.float32, device=DEV)
+    assert o.conv_out_gn(xd, ab, wp.to(DEV), 3, bias.to(DEV), out) is not None
+    torch.cuda.synchronize()
+    xn = Fn.group_norm(x.float().permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-6)
+    act = (xn * torch.sigmoid(xn)).bfloat16().float()
+    ref = Fn.conv2d(act, w.bfloat16().float(), bias, padding=1)
+    got = out.cpu()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    assert err <= 3e-3 * ref.abs().max().item(), (err, ref.abs().max().item())
