@@ -33,15 +33,29 @@ except Exception:                                       # pragma: no cover
 
 class _Node(nn.Module):
     """Anonymous container: the module tree only exists to give parameters their reference names."""
+    _pgt_root = None          # weak reference to the owning model (set by _materialise)
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        # loading into a submodule (e.g. model.conditionnet.load_state_dict(...), as the reference does for the
+        # face-parsing weights) must drop the root's packed-weight engine too
+        r = super().load_state_dict(state_dict, strict=strict, **kw)
+        root = self._pgt_root() if self._pgt_root is not None else None
+        if root is not None:
+            root._invalidate()
+        return r
 
 
 def _materialise(root, spec, seed):
+    import weakref
+    rootref = weakref.ref(root)
     for name, (shape, kind, dtype) in spec.items():
         parts = name.split('.')
         node = root
         for part in parts[:-1]:
             if part not in node._modules:
-                node.add_module(part, _Node())
+                child = _Node()
+                child._pgt_root = rootref
+                node.add_module(part, child)
             node = node._modules[part]
         t = synth_tensor(name, shape, 'codebook' if kind == 'codebook_ema' else kind, dtype, seed)
         if kind == 'codebook_ema':
@@ -80,6 +94,13 @@ class _B200Model(nn.Module):
         r = super().load_state_dict(state_dict, strict=strict, **kw)
         self._invalidate()
         return r
+
+    def refresh(self):
+        """Rebuilds the packed kernel-layout weights on the next forward.  load_state_dict() (on the model or any
+        submodule) and .to() / .cuda() do this automatically; call it after in-place edits of parameters
+        (`p.data.copy_(...)`, EMA swaps), which PyTorch gives no hook for."""
+        self._invalidate()
+        return self
 
     def engine(self):
         if self.__dict__.get('_engine') is None:

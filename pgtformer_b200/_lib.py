@@ -99,11 +99,13 @@ def load(build_if_missing=True):
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        if not build_if_missing:
-            raise RuntimeError('libpgt_b200.so not built: run `python -m pgtformer_b200.build`')
+    if build_if_missing:
+        # always goes through build(): it compares the source fingerprint with lib/build.stamp, so a stale binary next
+        # to a fresh checkout is rebuilt instead of silently loaded (a no-op when up to date, or without nvcc)
         from . import build as _build
         _build.build()
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError('libpgt_b200.so not built: run `python -m pgtformer_b200.build`')
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         try:

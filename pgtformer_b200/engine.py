@@ -20,6 +20,19 @@ from .spec import Arch
 BF = torch.bfloat16
 
 
+def _on_device(fn):
+    """Runs an Engine entry point with the engine's GPU as the current CUDA device: the C ABI launches on the current
+    device's current stream, and its per-device one-time setup (kernel attributes, constant tables) keys on it, so a model
+    on cuda:1 must not launch while cuda:0 is current."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        with torch.cuda.device(self.dev):
+            return fn(self, *a, **k)
+    return wrapper
+
+
 def _pack_conv(w):
     """OIHW fp32 -> [Cout, k*k*CinPad] bf16 (K index = tap*CinPad + c)."""
     co, ci, kh, kw = w.shape
@@ -71,8 +84,9 @@ class Engine:
         if self.dev.type != 'cuda':
             raise RuntimeError('pgtformer_b200 has no CPU path: the engine needs a CUDA (sm_100a) device')
         self.w = {}
-        self._sd = {k: v.detach().to(self.dev) for k, v in state_dict.items()}
-        self._repack()
+        with torch.cuda.device(self.dev):
+            self._sd = {k: v.detach().to(self.dev) for k, v in state_dict.items()}
+            self._repack()
 
     # ------------------------------------------------------------------ weight repack (load time)
     def _f32(self, name):
@@ -496,6 +510,7 @@ class Engine:
         return self._lin(y, 'idx_pred_layer.1', a.n_embed, out_dtype=torch.float32)
 
     # ------------------------------------------------------------------ full forwards
+    @_on_device
     @torch.no_grad()
     def forward(self, x, w=1.0, adain=True, code_only=False, force_codes=None, frame_index=None):
         """PGTFormer.forward (`archs/pgtformer_arch.py:598-714`).  x: fp32 [b*3,3,H,W] in [0,1] on the
@@ -546,6 +561,7 @@ class Engine:
         out = self.decoder(z.view(Fr, hh, ww, a.z_channels), feats, float(w))
         return out, logits5, lq_nhwc
 
+    @_on_device
     @torch.no_grad()
     def forward_graphed(self, x, w=1.0, adain=True):
         """The same launch sequence replayed from a CUDA graph captured once per (shape, w, adain): removes the
@@ -574,6 +590,7 @@ class Engine:
         graph.replay()
         return outs
 
+    @_on_device
     @torch.no_grad()
     def forward_vq(self, x, code_only=False):
         """TDCRQVAE3.forward (`archs/tdcrqvae3_arch.py:760-783`): encode -> L2 argmin -> embed -> decode."""

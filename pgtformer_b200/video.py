@@ -49,6 +49,10 @@ class VideoRestorer:
         into it.  Returns uint8 [count,H,W,3] on the device (the restored middle frames)."""
         eng = self.model.engine()
         Fd, H, W, _ = frames_u8_dev.shape
+        with torch.cuda.device(eng.dev):
+            return self._enqueue_on_device(eng, frames_u8_dev, local_windows, Fd, H, W)
+
+    def _enqueue_on_device(self, eng, frames_u8_dev, local_windows, Fd, H, W):
         x = ops.u8hwc_to_f32nchw(frames_u8_dev, torch.empty(Fd, 3, H, W, dtype=torch.float32, device=frames_u8_dev.device))
         idx = torch.tensor([j for win in local_windows for j in win], dtype=torch.int32).to(x.device, non_blocking=True)
         if self.reuse_frames:
@@ -80,7 +84,6 @@ class VideoRestorer:
         main = torch.cuda.current_stream(dev)
         copy = torch.cuda.Stream(dev)
         wins = window_indices(n)
-        pending = []                                   # (device result, first, count, ready event)
         staged = None                                  # frames of the NEXT batch already on their way
         plan = plan_batches(n, self.clips_per_batch)
 
@@ -105,9 +108,8 @@ class VideoRestorer:
             with torch.cuda.stream(copy):                            # D2H overlaps the next batch's compute
                 copy.wait_event(done)
                 out[first:first + cnt].copy_(res, non_blocking=True)
-            res.record_stream(copy)
+            res.record_stream(copy)                                  # the allocator keeps `res` until the copy has run
             d.record_stream(main)
-            pending.append(res)
         copy.synchronize()
         main.synchronize()
         return out.numpy()

@@ -66,3 +66,21 @@ def test_directory_written_by_the_reference_class_loads(network_g, tmp_path):
     assert set(rsd) == set(osd) and len(osd) == 961        # registration order differs, names do not
     for k in rsd:
         assert torch.equal(rsd[k], osd[k]), k
+
+
+def test_submodule_load_and_refresh_drop_the_packed_engine(network_g):
+    """The packed-weight engine is a derived cache: loading into a submodule (the reference loads the face-parsing
+    weights into `conditionnet` separately) or calling refresh() must invalidate it."""
+    from archs.pgtformer_arch import PGTFormer
+    kw = dict(network_g)
+    kw.pop('type')
+    m = PGTFormer(**kw)
+    marker = object()
+    m.__dict__['_engine'] = marker
+    m.conditionnet.load_state_dict(m.conditionnet.state_dict())
+    assert m.__dict__['_engine'] is None
+    m.__dict__['_engine'] = marker
+    m.encoder.down.load_state_dict(m.encoder.down.state_dict())
+    assert m.__dict__['_engine'] is None
+    m.__dict__['_engine'] = marker
+    assert m.refresh() is m and m.__dict__['_engine'] is None
