@@ -3,15 +3,15 @@
 // One CTA = one (clip, head) and TWO 128-query tiles (ping-pong groups G0/G1) that share the K/V stream:
 //   warp 0      TMA producer: Q tiles once, then K_j / V_j tiles (128 keys x 64, 128B swizzle) through a 3-deep ring
 //   warp 1      single-thread tcgen05.mma issuer:  S_g = Q_g K_j^T (128x128x64, fp32 in TMEM),
-//               O_g += P_g V_j (128x64x128; P_g bf16 in swizzled smem, V_j consumed MN-major straight from its TMA tile)
-//               and  L_g += P_g 1 (128x16x128 against a tile of ones): the softmax denominator comes off the tensor
-//               pipe, summed over exactly the bf16 P that the numerator uses
+//               [O_g | L_g] += P_g [V_j | 1] (128x80x128; P_g bf16 in swizzled smem, V_j consumed MN-major straight from
+//               its TMA tile, a second MN atom of ones appended through the descriptor's LBO): the softmax
+//               denominator comes off the tensor pipe, summed over exactly the bf16 P that the numerator uses
 //   warps 2..5  softmax group 0, warps 6..9 softmax group 1 (thread = query row): ONE pass over S per key tile —
 //               p = 2^(s*c - m_ref) against a reference exponent m_ref that is the row maximum of the first tile and is
 //               only raised (by a whole power of two, so the rescale of O and L in TMEM is exact) when a later tile
 //               produces p > 2^8; O and L stay in TMEM for the whole key loop and are read once at the end.
 // While group g runs its exponentials the tensor pipe works for the other group.
-// TMEM: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384) L0 [384,400) L1 [400,416).
+// TMEM: S0 [0,128) S1 [128,256) O0' [256,336) O1' [336,416), O' = [O (64) | L (16)].
 #include <cudaTypedefs.h>
 
 #include "common.cuh"
@@ -59,6 +59,9 @@ __device__ __forceinline__ void tmem_st_32x16_ft(uint32_t taddr, const uint32_t 
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void st_shared_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -66,10 +69,10 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 // MN-major (the N x K operand is stored K-rows x N-contiguous), 128B swizzle: 8 K-rows per 1024 B atom.
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes = 16384) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
-  d |= static_cast<uint64_t>((16384 >> 4) & 0x3FFF) << 16;    // LBO: stride between 64-element MN atoms (single atom here)
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;   // LBO: byte distance to the next 64-element MN atom
   d |= static_cast<uint64_t>((1024 >> 4) & 0x3FFF) << 32;     // SBO: stride between 8-row K groups
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
@@ -154,7 +157,9 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       for (int k = 0; k < FT_D / 16; ++k) umma_bf16_ss(tmem_base + g * FT_BN, da + 2 * k, db + 2 * k, idesc_s, k != 0 ? 1u : 0u);
       umma_commit(&s_full[g]);
     };
-    constexpr uint32_t idesc_l = umma_idesc_bf16(FT_BM, 16);                       // L: A = P, B = ones (layout-agnostic)
+    // O' = P [V | 1]: the B operand is the MN-major V tile (64 columns) followed, LBO bytes further, by an atom of
+    // ones (16 of its columns used), so columns 64..79 of the accumulator collect the row sums of P
+    constexpr uint32_t idesc_o80 = umma_idesc_bf16(FT_BM, FT_D + 16) | (1u << 16);
     auto issue_o = [&](int g, int st, uint32_t acc) {
 #pragma unroll
       for (int kt = 0; kt < 2; ++kt) {
@@ -162,16 +167,10 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           // 16 keys per step: +32 B inside P's swizzled row (K-major), +16 key rows = 2048 B in the V tile (MN-major)
-          const uint64_t db = umma_desc_mn_sw128(smem_u32(sV + st * FT_TILE + (kt * 64 + k * 16) * 128));
-          umma_bf16_ss(tmem_base + 256 + g * FT_D, da + 2 * k, db, idesc_o, (acc | kt | k) != 0 ? 1u : 0u);
+          const uint32_t vaddr = smem_u32(sV + st * FT_TILE + (kt * 64 + k * 16) * 128);
+          const uint64_t db = umma_desc_mn_sw128(vaddr, smem_u32(sOnes) - vaddr);
+          umma_bf16_ss(tmem_base + 256 + g * (FT_D + 16), da + 2 * k, db, idesc_o80, (acc | kt | k) != 0 ? 1u : 0u);
         }
-      }
-      const uint64_t dones = umma_desc_k_sw128(smem_u32(sOnes));
-#pragma unroll
-      for (int kt = 0; kt < 2; ++kt) {
-        const uint64_t da = umma_desc_k_sw128(smem_u32(sP + (g * 2 + kt) * FT_TILE));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + 384 + g * 16, da + 2 * k, dones + 2 * k, idesc_l, (acc | kt | k) != 0 ? 1u : 0u);
       }
       umma_commit(&o_full[g]);
     };
@@ -192,9 +191,11 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         if (g == 0 && j + 1 < NT) mbar_wait(&kv_full[nst], nph);
         tc_fence_after();
         if (elect_one()) {
+          // S of the next tile first: the softmax group starts on it while P V of this tile (needed only before the
+          // next P is written) runs behind it
+          if (j + 1 < NT) issue_s(g, nst);
           issue_o(g, st, j > 0 ? 1u : 0u);
           if (g == 1) umma_commit(&kv_empty[st]);      // every MMA reading K_j / V_j has been issued
-          if (j + 1 < NT) issue_s(g, nst);
         }
         __syncwarp();
       }
@@ -207,8 +208,8 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const int r = quad * 32 + lane;                      // query row inside the group's tile
     const uint32_t lane_base = uint32_t(quad * 32) << 16;
     const uint32_t tS = tmem_base + lane_base + g * FT_BN;
-    const uint32_t tO = tmem_base + lane_base + 256 + g * FT_D;
-    const uint32_t tL = tmem_base + lane_base + 384 + g * 16;
+    const uint32_t tO = tmem_base + lane_base + 256 + g * (FT_D + 16);
+    const uint32_t tL = tO + FT_D;                       // row sums: columns 64..79 of the O' accumulator
     uint8_t* prow = sP + g * 2 * FT_TILE + r * 128;
     const float sl2 = 0.125f * 1.4426950408889634f;     // d^-1/2 * log2(e)
     float mb = 0.f;                                      // reference exponent (log2 domain)
@@ -276,7 +277,7 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
       for (int q = 0; q < FT_BN / 8; ++q) {
         uint8_t* dst = prow + (q >> 3) * FT_TILE;            // key half (64 keys = one 128 B row of the sub-tile)
-        *reinterpret_cast<uint4*>(dst + (((q & 7) ^ (r & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        st_shared_v4(dst + (((q & 7) ^ (r & 7)) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       }
       tc_fence_before();
       fence_proxy_async();                                   // P (generic writes) -> visible to the tensor core's smem reads
