@@ -11,6 +11,8 @@ natural row order and no permute is ever materialised.
 Every op — including the BiSeNet parsing net, whose eval-mode BatchNorms are folded at load time — is a call
 into the C ABI; there is no PyTorch / cuDNN / CPU fallback: without the CUDA library construction fails.
 """
+import os
+
 import torch
 import torch.nn.functional as F  # noqa: F401  (load-time weight padding only)
 
@@ -141,7 +143,8 @@ class Engine:
     # GroupNorm+SiLU applied inside the consuming 3x3 conv (pgt_conv_gn_bf16, bit-identical).  Off by default: the
     # narrow (Cout <= 128) halo convs are bound by shared-memory operand reads, so the in-place slab transform costs
     # them more (+10 ms at 16 clips of 512^2) than the GroupNorm apply passes it removes (-6.8 ms); see DESIGN.md.
-    fuse_gn_apply = False
+    fuse_gn_apply = os.environ.get('PGT_FUSE_GN', '') != ''
+    fuse_gn_min_hw = int(os.environ.get('PGT_FUSE_GN', '0') or 0)       # fuse only for feature maps at least this tall
     fuse_gn_stats = True      # GroupNorm statistics from the producing conv / linear epilogue (saves one pass)
 
     def _gn(self, x, p, silu=True):
@@ -158,7 +161,7 @@ class Engine:
         stride = kw.get('stride', 1)
         fused_ab = None
         if gn is not None:
-            if self.fuse_gn_apply and stride == 1 and kw.get('ksize', 3) == 3 and kw.get('pad_lo', 1) == 1 and \
+            if self.fuse_gn_apply and H >= self.fuse_gn_min_hw and stride == 1 and kw.get('ksize', 3) == 3 and kw.get('pad_lo', 1) == 1 and \
                     'act' not in kw and not kw.get('relu_after_res') and ops.conv_gn_supported(H, W, cin, cout):
                 st = getattr(x, '_pgt_gn', None)
                 fused_ab = ops.groupnorm_ab(x, self.w[gn + '.weight'], self.w[gn + '.bias'],
