@@ -136,6 +136,8 @@ class Engine:
     def _new(self, *shape, dtype=BF):
         return torch.empty(*shape, dtype=dtype, device=self.dev)
 
+    fuse_cat_in_place = True  # SFT concat: encoder / decoder level outputs written straight into the concat buffer
+    _fusing = False           # set per forward: SFT fusion active (w > 0)
     fuse_conv_out = True      # decoder norm_out + SiLU + conv_out (64 -> 3) as one kernel (conv_out.cu)
     window_tc = True          # window attention core on TMA + tcgen05 (window_attn_tc.cu)
     fuse_ln_qkv = True        # norm1 + q/kv projection of the C=256 Swin blocks as one kernel
@@ -195,15 +197,15 @@ class Engine:
         return ops.linear(x, self.w[p + '.weight'], out, bias=self.w.get(p + '.bias'), N=n, gn_stats=stats, **kw)
 
     # ------------------------------------------------------------------ blocks
-    def td_resblock(self, x, p, cout, gn_next=False):
+    def td_resblock(self, x, p, cout, gn_next=False, out=None):
         """TDResnetBlock (`modules/rstt_layers.py:875-904`): 2 x (GN+SiLU -> conv3x3), residual in the
         second conv's epilogue (1x1 nin_shortcut first when the width changes).  conv1's epilogue also emits the
         GroupNorm statistics norm2 needs; with gn_next the block output carries them for the next Normalize()."""
         h = self._conv3(x, p + '.conv1', cout, gn=p + '.norm1', gn_out=True)
         sc = self._lin(x, p + '.nin_shortcut', cout) if (p + '.nin_shortcut.weight') in self.w else x
-        return self._conv3(h, p + '.conv2', cout, gn=p + '.norm2', residual=sc, gn_out=gn_next)
+        return self._conv3(h, p + '.conv2', cout, gn=p + '.norm2', residual=sc, gn_out=gn_next, out=out)
 
-    def swin_block(self, x, p, heads, shift, gn_next=False):
+    def swin_block(self, x, p, heads, shift, gn_next=False, out=None):
         """VSTSREncoderTransformerBlock (`modules/rstt_layers.py:284-338`) on [F,H,W,C]."""
         Fr, H, W, C = x.shape
         w = self.w
@@ -220,9 +222,9 @@ class Engine:
         x = self._lin(a, p + '.attn.proj', C, residual=x)
         if C == 256 and self.fuse_swin_mlp:
             # norm2 + fc1 + GELU + fc2 + residual in one kernel (the hidden tile never leaves the SM)
-            out = self._new(Fr, H, W, C)
+            out = self._new(Fr, H, W, C) if out is None else out
             stats = None
-            if gn_next and self.fuse_gn_stats and (H * W) % 128 == 0:
+            if gn_next and self.fuse_gn_stats and (H * W) % 128 == 0 and out.is_contiguous():
                 tpf = H * W // 128
                 stats = self._new(Fr * tpf * 4 * 64, dtype=torch.float32)
                 out._pgt_gn = (stats, tpf * 4)
@@ -231,13 +233,19 @@ class Engine:
                                 gn_stats=stats)
         y = ops.layernorm(x, w[p + '.norm2.weight'], w[p + '.norm2.bias'], self._new(Fr, H, W, C))
         m = self._lin(y, p + '.mlp.fc1', C, act=ops.ACT_GELU)
-        return self._lin(m, p + '.mlp.fc2', C, residual=x, gn_out=gn_next)
+        return self._lin(m, p + '.mlp.fc2', C, residual=x, gn_out=gn_next, out=out)
 
-    def encoder_layer(self, x, p, heads, depth, gn_next=False):
+    def encoder_layer(self, x, p, heads, depth, gn_next=False, out=None):
         for i in range(depth):
             x = self.swin_block(x, '%s.blocks.%d' % (p, i), heads, 2 if i % 2 == 1 else 0,
-                                gn_next=gn_next and i == depth - 1)
+                                gn_next=gn_next and i == depth - 1, out=out if i == depth - 1 else None)
         return x
+
+    def _cat_slot(self, Fr, H, W, C):
+        """Concat buffer [enc | dec | temporal] of a Fuse_sft_block level (`archs/pgtformer_arch.py:474`): the encoder
+        level and, later, the decoder level write their outputs straight into its channel slices, so `torch.cat` costs
+        no copy."""
+        return self._new(Fr, H, W, 2 * C + 32)
 
     def fuse_sft(self, enc, dec, key, wgt, gn_next=False):
         """Fuse_sft_block (`archs/pgtformer_arch.py:460-484`); the final
@@ -245,9 +253,11 @@ class Engine:
         p = 'fuse_convs_dict.' + key
         Fr, H, W, C = dec.shape
         b, P = Fr // 3, H * W
-        cat = self._new(Fr, H, W, 2 * C + 32)
-        ops.copy2d(enc, cat[..., :C])
-        ops.copy2d(dec, cat[..., C:2 * C])
+        cat = getattr(enc, '_pgt_cat', None)
+        if cat is None or getattr(dec, '_pgt_cat', None) is not cat:
+            cat = self._new(Fr, H, W, 2 * C + 32)                # streaming gather / foreign tensors: copy into place
+            ops.copy2d(enc, cat[..., :C])
+            ops.copy2d(dec, cat[..., C:2 * C])
         tcat = self._new(b, P, 192)
         ops.regroup_frames(self._lin(enc, p + '.tconvenc', 32), tcat[..., :96], b, P, 32, 0)
         ops.regroup_frames(self._lin(dec, p + '.tconvdec', 32), tcat[..., 96:], b, P, 32, 0)
@@ -397,15 +407,25 @@ class Engine:
     def _encoder_level(self, h, lvl, feats):
         a = self.arch
         last = lvl == a.num_levels - 1
+        Fr, H, W, _ = h.shape
+        # a level whose output is an SFT skip tensor writes it into the [enc | dec | t] concat buffer of that fusion
+        # (not the last level: its output carries GroupNorm statistics for mid.block_1 and must stay contiguous)
+        slot = None
+        if self.fuse_cat_in_place and self._fusing and lvl in a.fuse_level_key and not last:
+            cat = self._cat_slot(Fr, H, W, a.level_ch[lvl])
+            slot = cat[..., :a.level_ch[lvl]]
         for blk in range(a.num_res_blocks):
             # the next consumer of this level's output is a Normalize() only at the last level (mid.block_1);
             # otherwise it is the stride-2 Downsample conv, whose own epilogue feeds the next level's norm1
             nxt = last and blk == a.num_res_blocks - 1
+            fin = slot if blk == a.num_res_blocks - 1 else None
             h = self.td_resblock(h, 'encoder.down.%d.block.%d' % (lvl, blk), a.level_ch[lvl],
-                                 gn_next=nxt and not a.level_has_attn[lvl])
+                                 gn_next=nxt and not a.level_has_attn[lvl], out=None if a.level_has_attn[lvl] else fin)
             if a.level_has_attn[lvl]:
                 h = self.encoder_layer(h, 'encoder.down.%d.attn.%d' % (lvl, blk), a.num_heads[lvl], a.depths[lvl],
-                                       gn_next=nxt)
+                                       gn_next=nxt, out=fin)
+        if slot is not None:
+            h._pgt_cat = cat
         feats.append(h)
         if not last:
             h = self._conv3(h, 'encoder.down.%d.downsample.conv' % lvl, a.level_ch[lvl], stride=2, pad_lo=0, gn_out=True)
@@ -448,15 +468,20 @@ class Engine:
         for lvl in reversed(range(a.num_levels)):
             nblk = a.num_res_blocks + 1
             fuse = feats is not None and lvl in a.fuse_level_key and wgt > 0
+            cat = getattr(feats[lvl], '_pgt_cat', None) if fuse else None
             for blk in range(nblk):
                 # next consumer is a Normalize(): the next block of this level, or decoder.norm_out after the very
                 # last block; after the level's last block comes the SFT concat / the upsample conv instead
                 nxt = blk < nblk - 1 or (lvl == 0 and not fuse)
-                h = self.td_resblock(h, 'decoder.up.%d.block.%d' % (lvl, blk), a.level_ch[lvl],
-                                     gn_next=nxt and not a.level_has_attn[lvl])
+                C = a.level_ch[lvl]
+                fin = cat[..., C:2 * C] if (cat is not None and blk == nblk - 1) else None
+                h = self.td_resblock(h, 'decoder.up.%d.block.%d' % (lvl, blk), C,
+                                     gn_next=nxt and not a.level_has_attn[lvl], out=None if a.level_has_attn[lvl] else fin)
                 if a.level_has_attn[lvl]:
                     h = self.encoder_layer(h, 'decoder.up.%d.attn.%d' % (lvl, blk), a.num_heads[lvl], a.depths[lvl],
-                                           gn_next=nxt)
+                                           gn_next=nxt, out=fin)
+                if fin is not None:
+                    h._pgt_cat = cat
             if fuse:
                 h = self.fuse_sft(feats[lvl], h, a.fuse_level_key[lvl], wgt, gn_next=(lvl == 0))
             if lvl != 0:
@@ -532,6 +557,7 @@ class Engine:
         hh, ww = H // 16, W // 16
         T, E = Fr * hh * ww, a.dim_embd
         wd = self.w
+        self._fusing = (not code_only) and float(w) > 0 and frame_index is None
         pos = self.parse_pos(x)
         # encoder
         if frame_index is None:
@@ -602,6 +628,7 @@ class Engine:
         Fr, _, H, W = x.shape
         hh, ww = H // 16, W // 16
         T = Fr * hh * ww
+        self._fusing = False                                   # the plain autoencoder has no SFT fusion
         h, _ = self.encoder(x)
         z_e = self._lin(h.view(T, -1), 'quant_conv', a.embed_dim, out_dtype=torch.float32)
         codes = torch.empty(T, dtype=torch.int64, device=self.dev)

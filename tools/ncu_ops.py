@@ -53,5 +53,54 @@ elif which == 'swin_mlp':
     out = torch.empty_like(x)
     for _ in range(3):
         ops.swin_mlp(x, g, b, w1, b, w2, b, out)
+elif which == 'window_tc':
+    from pgtformer_b200.weights import relative_position_index
+    C, H, clips, heads = 256, 128, 4, 8
+    T = clips * 3 * H * H
+    qkv = torch.randn(T, 3 * C, device=dev).bfloat16()
+    bias = (0.02 * torch.randn(245, heads, device=dev))[relative_position_index().view(-1).to(dev)].view(48, 48, heads)
+    tab = ops.window_tables(bias.permute(2, 0, 1).contiguous())
+    out = torch.empty(T, C, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.window_attention_tc(qkv, clips, H, H, C, heads, 2, tab, out)
+elif which == 'mha_tc':
+    clips, L, E = 4, 3072, 512
+    q, k, v = (torch.randn(clips * L, E, device=dev).bfloat16() for _ in range(3))
+    out = torch.empty(clips * L, E, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.mha(q, k, v, clips, L, 8, 64, out)
+elif which == 'argmax':
+    T = 49152
+    logits = torch.randn(T, 1024, device=dev)
+    cb = torch.randn(1025, 512, device=dev)
+    idx = torch.empty(T, dtype=torch.int64, device=dev)
+    quant = torch.empty(T, 512, device=dev)
+    for _ in range(3):
+        ops.argmax_gather(logits, cb, idx, quant)
+elif which == 'l2_argmin':
+    T = 49152
+    cb = torch.randn(1025, 512, device=dev)
+    z = torch.randn(T, 512, device=dev)
+    idx = torch.empty(T, dtype=torch.int64, device=dev)
+    pack = ops.codebook_pack(cb, 1024)
+    for _ in range(3):
+        ops.l2_argmin_tc(z, cb, pack, 1024, idx, None)
+elif which == 'ln_linear':
+    M = 786432 // 4
+    x = torch.randn(M, 256, device=dev).bfloat16()
+    w = (torch.randn(768, 256, device=dev) * 0.05).bfloat16()
+    g, b = torch.ones(256, device=dev), torch.zeros(256, device=dev)
+    bias = torch.zeros(768, device=dev)
+    out = torch.empty(M, 768, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.ln_linear(x, g, b, w, bias, out)
+elif which == 'conv_out':
+    x = torch.randn(F, 512, 512, 64, device=dev).bfloat16()
+    g, b = torch.ones(64, device=dev), torch.zeros(64, device=dev)
+    ab = ops.groupnorm_ab(x, g, b, torch.empty(F * 128, device=dev))
+    w = _pack_conv(torch.randn(3, 64, 3, 3, device=dev) * 0.05)
+    out = torch.empty(F, 3, 512, 512, device=dev)
+    for _ in range(3):
+        ops.conv_out_gn(x, ab, w, 3, torch.zeros(3, device=dev), out)
 torch.cuda.synchronize()
 print('done', which)

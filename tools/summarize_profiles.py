@@ -91,7 +91,16 @@ KEYS = [
     ('sm__cycles_elapsed.max', 'SM cycles'),
 ]
 
-OPS = [('halo64', 'conv_halo_kernel<64>: 3x3, 12 frames 512^2, Cin=Cout=64, residual (weights resident)'),
+KEYS += [('sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'XU (MUFU) pipe %'),
+         ('smsp__issue_active.avg.pct_of_peak_sustained_active', 'issue slots busy %')]
+
+OPS = [('window_tc', 'window_attn_tc_kernel<32>: 4 clips x 1024 shifted windows of 48 tokens, C=256, 8 heads (core only: HBM-bound, 24 FLOP/B)'),
+       ('mha_tc', 'mha_tc_kernel: 4 clips, L=3072, 8 heads x d=64 (flash attention, O / L in TMEM)'),
+       ('argmax', 'argmax_gather_kernel: T=49152 rows x 1024 fp32 logits + gather of 512-float codes'),
+       ('l2_argmin', 'l2_argmin_tc_kernel: T=49152 tokens x 1024 codes x 512 (bf16 tensor-core scores + certified window)'),
+       ('ln_linear', 'ln_linear_kernel: LayerNorm + q/kv projection, T=196608, C=256 -> 768'),
+       ('conv_out', 'conv_out_gn_kernel: norm_out + SiLU + conv 64->3, 12 frames 512^2, fp32 NCHW output'),
+       ('halo64', 'conv_halo_kernel<64>: 3x3, 12 frames 512^2, Cin=Cout=64, residual (weights resident)'),
        ('halo128', 'conv_halo2_kernel<128> (CTA pairs): 3x3, 12 frames 256^2, Cin=Cout=128, residual'),
        ('conv256', 'gemm_tc_kernel<256, pair>: 3x3, 12 frames 128^2, Cin=Cout=256 (K=2304), residual'),
        ('linear256', 'gemm_tc_kernel<256>: linear M=196608 N=256 K=256 + residual (HBM / L2 bound)'),
@@ -120,7 +129,70 @@ def ops():
     print('\n'.join(out[:40]))
 
 
+def traffic():
+    """dram bytes per launch of the dominant (tcgen05 GEMM / conv) class over one forward -> profiles/<tag>_traffic.json"""
+    import json
+    path = os.path.join(SRC, 'traffic.csv.gz')
+    if not os.path.exists(path):
+        print('no traffic capture')
+        return
+    text = gzip.open(path, 'rt').read()
+    start = text.index('"ID"')
+    per = collections.OrderedDict()
+    for r in csv.DictReader(io.StringIO(text[start:])):
+        d = per.setdefault(r['ID'], {'k': short(r['Kernel Name'])})
+        v = float(r['Metric Value'].replace(',', ''))
+        u = r['Metric Unit']
+        if r['Metric Name'].startswith('dram__bytes'):
+            mult = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1)
+            d['bytes'] = d.get('bytes', 0.0) + v * mult
+        elif r['Metric Name'] == 'gpu__time_duration.sum':
+            d['ms'] = v / 1e6 if u in ('ns', 'nsecond') else v / 1e3 if u in ('us', 'usecond') else v
+    seq = list(per.values())
+    marks = [i for i, d in enumerate(seq) if 'argmax_gather' in d['k']]
+    if len(marks) < 2:
+        print('cannot delimit forwards')
+        return
+    one = seq[marks[-2] + 1: marks[-1] + 1]
+    cls = [d for d in one if re.search(r'gemm_tc|conv_halo|swin_mlp|rgb_conv|ln_linear|conv_out_gn', d['k'])]
+    tot_b = sum(d.get('bytes', 0.0) for d in cls)
+    allb = sum(d.get('bytes', 0.0) for d in one)
+    out = {'source': 'ncu dram__bytes_read.sum + dram__bytes_write.sum, one forward of `bench.py --steps 1 --warmup 3` '
+                     '(16 clips 3x512x512), launches of the tcgen05 GEMM / conv class',
+           'launches': len(cls), 'dram_bytes_per_launch': tot_b / max(len(cls), 1), 'dram_bytes_class_per_step': tot_b,
+           'dram_bytes_all_kernels_per_step': allb, 'launches_all': len(one),
+           'class_ms_serialised': sum(d.get('ms', 0.0) for d in cls)}
+    # algorithmic bytes of the class from the per-launch shapes of layers.txt (inputs + outputs + residual + weights, bf16)
+    lay = os.path.join(SRC, 'layers.txt')
+    if os.path.exists(lay):
+        alg = 0.0
+        n = 0
+        for line in open(lay):
+            m = re.match(r'\s*(\S.*?)\s+n=\s*(\d+)\s', line)
+            if not m:
+                continue
+            desc, cnt = m.group(1), int(m.group(2))
+            g = {k: int(v) for k, v in re.findall(r'\b([FHWKNM])(\d+)\b', desc)}
+            if 'M' in g:
+                M, N, K = g['M'], g.get('N', 0), g.get('K', 0)
+                b = M * K * 2 + M * N * 2 + N * K * 2
+            elif 'F' in g and 'H' in g:
+                M = g['F'] * g['H'] * g['W']
+                N, K = g.get('N', 0), g.get('K', 0)
+                taps = 9 if desc.startswith(('halo3', 'conv3', 'conv_out')) else 4 if desc.startswith('conv2') else 1
+                b = M * (K // taps) * 2 + M * N * 2 + N * K * 2 + (M * N * 2 if ' r1' in desc else 0)
+            else:
+                continue
+            alg += b * cnt
+            n += cnt
+        out['algorithmic_bytes_class_per_step'] = alg
+        out['algorithmic_bytes_per_launch'] = alg / max(n, 1)
+    json.dump(out, open(os.path.join(DST, '%s_traffic.json' % tag), 'w'), indent=1)
+    print(json.dumps(out, indent=1))
+
+
 launches()
+traffic()
 if os.path.exists(os.path.join(SRC, 'layers.txt')):
     shutil.copy(os.path.join(SRC, 'layers.txt'), os.path.join(DST, '%s_layers_b16.txt' % tag))
 ops()
