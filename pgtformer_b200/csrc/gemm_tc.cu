@@ -1438,7 +1438,7 @@ static int conv_impl(const void* x, int F, int Hin, int Win, int Cin, int ldx, c
     p.mode = MODE_CONV_S1;
     p.H = Hin; p.W = Win;
   } else {
-    if ((Hin & 1) || (Win & 1) || (Cin % BK) != 0 || ldx != Cin) return PGT_ERR_UNSUPPORTED;
+    if ((Hin & 1) || (Win & 1) || (Cin % BK) != 0 || ldx < Cin) return PGT_ERR_UNSUPPORTED;   // ldx > Cin: channel-slice view of a wider buffer
     p.mode = MODE_CONV_S2;
     p.H = Hin / 2; p.W = Win / 2;
     p.cin_ld = ldx;
