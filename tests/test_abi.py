@@ -39,3 +39,16 @@ def test_status_strings_and_arg_validation():
         raise AssertionError('check() must raise')
     except RuntimeError as e:
         assert 'not covered' in str(e)
+
+
+def test_torch_library_shim_registers_the_ops():
+    """`torch.ops.pgt.*` (pgtformer_b200/csrc_torch/pgt_torch_ops.cpp) builds, loads and registers its schemas — no
+    compute without a GPU."""
+    import torch
+    from pgtformer_b200 import torch_ops
+    ns = torch_ops.load()
+    for name in ('window_attention', 'mha_fwd', 'argmax_gather', 'codebook_pack', 'l2_argmin', 'linear'):
+        op = getattr(ns, name)
+        assert 'pgt::' + name in str(op.default._schema)
+    with __import__('pytest').raises(Exception):              # CPU tensors: no kernel registered for that backend
+        torch.ops.pgt.codebook_pack(torch.zeros(8, 8), 8)

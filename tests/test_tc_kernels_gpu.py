@@ -224,3 +224,54 @@ def test_conv_out_gn_fused(F, H, W):
     assert torch.isfinite(got).all()
     err = (got - ref).abs().max().item()
     assert err <= 3e-3 * ref.abs().max().item(), (err, ref.abs().max().item())
+
+
+# ------------------------------------------------------------------------------------ TORCH_LIBRARY binding
+def test_torch_ops_binding_equals_ctypes_binding(synth_sd):
+    """torch.ops.pgt.* and the ctypes binding call the same C entry points: identical bits."""
+    from pgtformer_b200 import torch_ops
+    from pgtformer_b200.weights import relative_position_index
+    o = ops()
+    t = torch_ops.load()
+    # window attention
+    C, H, W, clips, heads = 256, 16, 16, 2, 8
+    T = clips * 3 * H * W
+    qkv = rnd((T, 3 * C), 1).bfloat16().to(DEV)
+    bias = (0.5 * rnd((245, heads), 2))[relative_position_index().view(-1)].view(48, 48, heads).permute(2, 0, 1).contiguous().to(DEV)
+    tab = o.window_tables(bias)
+    a = torch.empty(T, C, dtype=torch.bfloat16, device=DEV)
+    b = torch.empty_like(a)
+    o.window_attention_tc(qkv, clips, H, W, C, heads, 2, tab, a)
+    t.window_attention(qkv, clips, H, W, C, heads, 2, tab, b)
+    assert torch.equal(a, b)
+    # codebook kernels
+    cb = synth_sd['quantizer.codebooks.0.weight'].to(DEV).contiguous()
+    z = rnd((1000, 512), 3).to(DEV)
+    i1 = torch.empty(1000, dtype=torch.int64, device=DEV)
+    i2 = torch.empty_like(i1)
+    o.l2_argmin_tc(z, cb, o.codebook_pack(cb, 1024), 1024, i1)
+    cb16, norm = t.codebook_pack(cb, 1024)
+    t.l2_argmin(z, cb, cb16, norm, 1024, i2, None)
+    assert torch.equal(i1, i2)
+    logits = rnd((1000, 1024), 4).to(DEV)
+    q1, q2 = torch.empty(1000, 512, device=DEV), torch.empty(1000, 512, device=DEV)
+    o.argmax_gather(logits, cb, i1, q1)
+    t.argmax_gather(logits, cb, i2, q2)
+    assert torch.equal(i1, i2) and torch.equal(q1, q2)
+    # GEMM with bias + GELU + residual, flash attention
+    x = rnd((300, 192), 5).bfloat16().to(DEV)
+    w = rnd((96, 192), 6, 0.1).bfloat16().to(DEV)
+    bia = rnd((96,), 7).to(DEV)
+    res = rnd((300, 96), 8).bfloat16().to(DEV)
+    y1 = torch.empty(300, 96, dtype=torch.bfloat16, device=DEV)
+    y2 = torch.empty_like(y1)
+    o.linear(x, w, y1, bias=bia, act=o.ACT_GELU, residual=res)
+    t.linear(x, w, bia, o.ACT_GELU, res, y2)
+    assert torch.equal(y1, y2)
+    L = 256
+    q, k, v = (rnd((2 * L, 512), 9 + i).bfloat16().to(DEV) for i in range(3))
+    m1 = torch.empty(2 * L, 512, dtype=torch.bfloat16, device=DEV)
+    m2 = torch.empty_like(m1)
+    o.mha(q, k, v, 2, L, 8, 64, m1)
+    t.mha_fwd(q, k, v, 2, L, 8, 64, m2)
+    assert torch.equal(m1, m2)
