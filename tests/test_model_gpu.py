@@ -187,9 +187,10 @@ def test_vq_path_codes_against_reference_golden(model):
 
 
 def test_batch_equals_per_clip(model):
-    """Clips are independent: a b=2 forward equals two b=1 forwards (our kernels are
-    bit-deterministic per clip; the cuDNN parsing net may pick batch-dependent algorithms, hence
-    a tolerance instead of torch.equal)."""
+    """Clips are independent: a b=2 forward equals two b=1 forwards.  Bit-identity across batch sizes is
+    asserted for the encoder output (lq_feat) and for the decoder output under forced codes; the logits, which also
+    depend on the parsing branch (tiny feature maps whose tile / frame alignment changes with the batch), are compared
+    with a tolerance."""
     x = torch.rand(6, 3, 64, 64, generator=torch.Generator().manual_seed(11)).to(DEV)
     lo, lq = model(x, w=1, adain=True, code_only=True)
     lo0, lq0 = model(x[:3], w=1, adain=True, code_only=True)
