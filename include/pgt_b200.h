@@ -209,6 +209,16 @@ int pgt_window_attention(const void* qkv, int ldqkv, int clips, int H, int W, in
 int pgt_window_attention_tc(const void* qkv, int ldqkv, int clips, int H, int W, int C, int heads, int shift,
                             const void* tab, void* out, int ldo, int mode_n64, void* stream);
 
+/* ---- generic 3-D shifted-window attention core of the Video-Swin BasicLayer (window3d.cu; modules/swin.py:136-166,
+ * 214-250, 309-323; used by TDRQVAE, archs/tdrqvae_arch.py:834-835): window (wd, wh, ww) with wd*wh*ww <= 128, shift
+ * (sd, sh, sw), feature map [B, D, H, W] zero-padded to multiples of the window AFTER the projection of the normalised
+ * tokens (pad_qkv = the qkv projection of a zero token, i.e. its bias, or NULL for zeros), get_window_size applied
+ * here.  qkv bf16 [B*D*H*W, ldqkv] (q | k | v); bias fp32 [heads, N, N] = relative_position_bias_table[
+ * relative_position_index[:N, :N]]; out bf16 [B*D*H*W, ldo].  Head dims 16 / 32 / 64. */
+int pgt_window3d_attention(const void* qkv, int ldqkv, const void* pad_qkv, int B, int D, int H, int W, int C, int heads,
+                           int wd, int wh, int ww, int sd, int sh, int sw, const float* bias, void* out, int ldo,
+                           void* stream);
+
 /* ---- global multi-head attention (flash-attention forward, no mask), per clip:
  * q,k,v: bf16 [clips*L, ld*] with head h at columns [h*d, (h+1)*d); out bf16 [clips*L, ldo].
  * Replaces the nn.MultiheadAttention core (archs/codeformer_arch.py:105,129-130); the

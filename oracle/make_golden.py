@@ -6,6 +6,7 @@ Run in the build container (the reference does not exist on the GPU box):
     python -m oracle.make_golden            # 128^2 fixtures (full tensors)
     python -m oracle.make_golden --full     # 512^2 (the reference's native size, NO size patch) and 1024^2 (size patch)
     python -m oracle.make_golden --video    # first 8 frames of assets/inputdemovideo.mp4 through inference.py's loop
+    python -m oracle.make_golden --swin     # the Video-Swin BasicLayer of modules/swin.py (TDRQVAE) on stand-in weights
 Inputs are not stored: `golden_input(seed, b, H)` regenerates them bit-exactly.
 
 The full-size fixtures are stored compactly (the raw outputs are 50-200 MB): every code index (int16), the top-2
@@ -154,14 +155,38 @@ def video(n=8):
     print('wrote %s in %.0f s (%.1f MB)' % (path, time.time() - t0, os.path.getsize(path) / 1e6), frames.shape, restored.shape)
 
 
+def swin():
+    """The reference's Video-Swin `BasicLayer` (`modules/swin.py:326-405`, imported with the mmcv / basicsr / timm shims)
+    on the deterministic stand-in weights of oracle/swin3d_oracle.py: outputs stored as fp16."""
+    import importlib.util
+    from oracle import swin3d_oracle as S
+    from oracle.reference_loader import REFERENCE_ROOT, _ensure_paths
+    _ensure_paths()
+    spec = importlib.util.spec_from_file_location('_pgt_reference.modules.swin', os.path.join(REFERENCE_ROOT, 'modules', 'swin.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for name, c in S.SWIN_CASES.items():
+        layer = mod.BasicLayer(c['dim'], c['depth'], c['heads'], c['window']).eval()
+        layer.load_state_dict(S.synth_state(layer.state_dict(), c['seed']), strict=True)
+        x = S.case_input(name)
+        with torch.no_grad():
+            y = layer(x)
+        path = os.path.join(GOLDEN, 'swin3d_%s.pt' % name)
+        torch.save({'case': name, 'out': y.to(torch.float16), 'out_absmax': y.abs().max().item()}, path)
+        print('wrote', path, tuple(y.shape), '%.1f KB' % (os.path.getsize(path) / 1e3))
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--full', action='store_true')
     ap.add_argument('--video', action='store_true')
+    ap.add_argument('--swin', action='store_true')
     a = ap.parse_args()
     if a.full:
         full()
     if a.video:
         video()
-    if not (a.full or a.video):
+    if a.swin:
+        swin()
+    if not (a.full or a.video or a.swin):
         small()

@@ -64,6 +64,8 @@ SIGNATURES = {
                                      c_int, c_void_p]),
     'pgt_window_attention_tc': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                         c_int, c_int, c_void_p]),
+    'pgt_window3d_attention': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                       c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     'pgt_mha_fwd': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                             c_int, c_void_p]),
     'pgt_argmax_gather': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,

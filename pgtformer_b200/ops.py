@@ -306,6 +306,16 @@ def window_attention_tc(qkv, clips, H, W, C, heads, shift, tab16, out, mode_n64=
     return out
 
 
+def window3d_attention(qkv, B, D, H, W, C, heads, window, shift, bias, out, pad_qkv=None):
+    """Generic 3-D shifted-window attention core (Video-Swin BasicLayer of TDRQVAE); bias fp32 [heads, N, N]."""
+    lib = L.load()
+    assert qkv.dtype == torch.bfloat16 and bias.dtype == torch.float32 and bias.is_contiguous()
+    L.check(lib.pgt_window3d_attention(_p(qkv), _rows(qkv)[2], _p(pad_qkv), B, D, H, W, C, heads, window[0], window[1],
+                                       window[2], shift[0], shift[1], shift[2], _p(bias), _p(out), _rows(out)[2],
+                                       _stream(qkv)))
+    return out
+
+
 def mha(q, k, v, clips, L_, heads, d, out):
     lib = L.load()
     L.check(lib.pgt_mha_fwd(_p(q), _rows(q)[2], _p(k), _rows(k)[2], _p(v), _rows(v)[2], clips, L_, heads, d, _p(out),
