@@ -188,6 +188,24 @@ def test_l2_argmin_tc_bit_exact_baseline_sizes(synth_sd, regime, T):
     assert torch.equal(quant[::97], cb[ref[::97]])
 
 
+@pytest.mark.parametrize('K,E,T', [(768, 512, 40000), (512, 256, 33333), (256, 128, 700), (1024, 384, 20001)])
+def test_l2_argmin_tc_other_codebook_shapes(synth_sd, K, E, T):
+    """Pair sweep with an odd number of N-tiles (the accumulator buffers alternate across tiles), fewer k-blocks, several
+    256-token tiles per CTA pair and a ragged last tile (one CTA of the last pair entirely past T)."""
+    o = ops()
+    cb = synth_sd['quantizer.codebooks.0.weight'][:K, :E].contiguous()
+    z = rnd((T, E), 31 + K)
+    cbd = cb.to(DEV)
+    idx = torch.full((T,), -7, dtype=torch.int64, device=DEV)
+    quant = torch.empty(T, E, dtype=torch.float32, device=DEV)
+    o.l2_argmin_tc(z.to(DEV), cbd, o.codebook_pack(cbd, K), K, idx, quant)
+    torch.cuda.synchronize()
+    ref = fp64_argmin_big(cb, z)
+    bad = int((idx.cpu() != ref).sum())
+    assert bad == 0, '%d mismatches vs the fp64 argmin (K=%d E=%d T=%d)' % (bad, K, E, T)
+    assert torch.equal(quant.cpu()[::53], cb[ref[::53]])
+
+
 def test_l2_argmin_tc_equals_exhaustive_kernel(synth_sd):
     o = ops()
     cb = synth_sd['quantizer.codebooks.0.weight'].to(DEV).contiguous()
