@@ -292,6 +292,8 @@ def main():
         main_stream.wait_stream(h2d_stream)
         xd.record_stream(main_stream)
         out = model(xd, w=1, adain=True)[0]
+        if model.cuda_graph:
+            out = out.clone()                                   # the graph's static output is rewritten by the next replay
         gathered = collective(out)                              # N > 1: the collective is part of the end-to-end step too
         d2h_stream.wait_stream(main_stream)
         with torch.cuda.stream(d2h_stream):
@@ -323,6 +325,13 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    # kernels per forward, counted by the library on an eager forward (a graph replay launches the same kernels without
+    # passing through the C ABI's launch counter)
+    model.cuda_graph = False
+    ops.reset_launch_count()
+    model(x_dev, w=1, adain=True)
+    launches_per_forward = ops.launch_count()
+    model.cuda_graph = bool(args.graph)
     for _ in range(warmup):
         step_resident()
     sampler = ClockSampler(local)
@@ -330,7 +339,7 @@ def main():
         sampler.start()
     ops.reset_launch_count()
     ms = timed(step_resident, args.steps)
-    launches = ops.launch_count()
+    launches = ops.launch_count() if not args.graph else launches_per_forward * args.steps
     clocks = sampler.stop() if rank == 0 else None
     value = world * b * args.steps / (ms / 1000.0)
 

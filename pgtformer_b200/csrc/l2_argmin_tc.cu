@@ -29,10 +29,6 @@
 //   duplicated / zero rows) are appended to a list for the exhaustive fp32+fp64 kernel in codebook.cu.
 // The result therefore equals an fp64 argmin of ||z - e_k||^2 with first-index tie-break for every input.
 #include <float.h>
-#include <stdio.h>
-#include <stdlib.h>
-
-#include <vector>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -269,8 +265,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LT_THREADS, 1)
 l2_argmin_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const float* __restrict__ z, const float2* __restrict__ zn2, int T, int E,
                       const float* __restrict__ cb, const float* __restrict__ norm, int K, int64_t* __restrict__ idx,
-                      float* __restrict__ quant, int* __restrict__ fb_count, int* __restrict__ fb_list,
-                      unsigned long long* dbg) {
+                      float* __restrict__ quant, int* __restrict__ fb_count, int* __restrict__ fb_list) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                                          // [E/64][128 rows][128 B]: this CTA's 128 tokens
@@ -400,35 +395,19 @@ l2_argmin_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
       float runmin = live ? FLT_MAX : -FLT_MAX, thr = runmin;  // rows past T never pass the chunk test
       int cnt = 0;
-      auto stamp = [&](int k) {
-        if (dbg != nullptr && threadIdx.x == 64 && it < 4) {
-          unsigned long long tt;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
-          dbg[(blockIdx.x * 4 + it) * 8 + k] = tt;
-        }
-      };
-      stamp(0);
       for (int nt = 0; nt < NT; ++nt) {
         if (((it * NT + nt) & 1) != g) continue;
-        const long long c0 = clock64();
         mbar_wait(&t_full[g], use & 1);
-        const long long c1 = clock64();
         ++use;
         tc_fence_after();
         argmin_scan_ntile(tacc, norm + nt * LT_BN, nt * LT_BN, W, smem_u32(lst), runmin, thr, cnt);
-        if (dbg != nullptr && threadIdx.x == 64 && it < 4) {
-          dbg[(blockIdx.x * 4 + it) * 8 + 5] += (unsigned long long)(c1 - c0);
-          dbg[(blockIdx.x * 4 + it) * 8 + 6] += (unsigned long long)(clock64() - c1);
-        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(te);                // one cluster-scope arrive per warp
       }
-      stamp(1);
       // merge: every thread filters its own list against the row's minimum over both warpgroups
       xmin[g * LT_BM + r] = runmin;
       named_bar_sync(1, 256);
-      stamp(2);
       {
         const float win = fminf(xmin[r], xmin[LT_BM + r]) + W;
         if (cnt > LT_LIST) ovf[r] = 1;
@@ -442,7 +421,6 @@ l2_argmin_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
       }
       named_bar_sync(1, 256);
-      stamp(3);
       // resolution: warp w8 owns rows w8 + 8 i; lane i < 16 looks at row i, windows of one code (the usual case) are done
       // there and then, the others go through the warp-wide exact evaluation one after the other
       {
@@ -480,7 +458,6 @@ l2_argmin_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           }
         }
       }
-      stamp(4);
     }
   }
 
@@ -544,29 +521,21 @@ extern "C" int pgt_l2_argmin_tc(const float* z, int T, int E, const float* codeb
   const int npairs = n_pt < num_sms() / 2 ? n_pt : num_sms() / 2;
   {
     ProfScope ps(PGT_PROF_ARGMIN, 2.0 * T * (double)K * E, st, "l2_argmin_tc");
-    z_pack_kernel<<<num_sms() * 2, 256, 0, st>>>(z, T, E, zb, zn2);
-    static const bool dbg_on = getenv("PGT_ARGMIN_DBG") != nullptr;
-    unsigned long long* dbg = nullptr;
-    if (dbg_on) { cudaMalloc(&dbg, 2 * npairs * 4 * 8 * 8); cudaMemset(dbg, 0, 2 * npairs * 4 * 8 * 8); }
-    l2_argmin_pair_kernel<<<2 * npairs, LT_THREADS, LT_SMEM, st>>>(tmA, tmB, z, zn2, T, E, codebook, cb_norm, K, idx, quant,
-                                                                   fb_count, fb_list, dbg);
-    PGT_LAUNCH_OK();
-    if (dbg_on) {
-      cudaDeviceSynchronize();
-      std::vector<unsigned long long> h(2 * npairs * 4 * 8);
-      cudaMemcpy(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost);
-      cudaFree(dbg);
-      unsigned long long t00 = ~0ull;
-      for (size_t i = 0; i < h.size(); ++i) if (h[i] != 0 && h[i] < t00) t00 = h[i];
-      for (int c : {0, 1, 2 * npairs - 1}) {
-        for (int it = 0; it < 4; ++it) {
-          const unsigned long long* e = &h[(c * 4 + it) * 8];
-          if (e[0] == 0) continue;
-          fprintf(stderr, "argmin dbg cta %d tile %d: start %+.1f us, scan %.1f (wait %.0f clk, compute %.0f clk), bar %.1f, merge %.1f, resolve %.1f\n", c, it,
-                  (e[0] - t00) / 1e3, (e[1] - e[0]) / 1e3, (double)e[5], (double)e[6], (e[2] - e[1]) / 1e3, (e[3] - e[2]) / 1e3, (e[4] - e[3]) / 1e3);
-        }
+    // pack grid: warps take 4 rows per step; pick the CTA count in [SMs, 2 SMs] that leaves the smallest ragged last step
+    int pack_ctas = num_sms() * 2;
+    {
+      const long long items = ceil_div(T, 4);
+      long long best_waste = -1;
+      for (int c = num_sms() * 2; c >= num_sms(); --c) {
+        const long long w = (long long)c * 8;
+        const long long waste = ((items + w - 1) / w) * w - items;
+        if (best_waste < 0 || waste < best_waste) { best_waste = waste; pack_ctas = c; }
       }
     }
+    z_pack_kernel<<<pack_ctas, 256, 0, st>>>(z, T, E, zb, zn2);
+    l2_argmin_pair_kernel<<<2 * npairs, LT_THREADS, LT_SMEM, st>>>(tmA, tmB, z, zn2, T, E, codebook, cb_norm, K, idx, quant,
+                                                                   fb_count, fb_list);
+    PGT_LAUNCH_OK();
   }
   // tokens whose certificate window did not fit the shortlist (degenerate codebooks): exhaustive exact kernel
   return l2_argmin_list_launch(z, T, E, codebook, K, idx, quant, fb_list, fb_count, num_sms(), st);

@@ -24,7 +24,7 @@ for op in halo64 halo128 conv256 linear256 swin_mlp rgb gn window_tc mha_tc argm
     window_tc) rx='regex:window_attn_tc' ;;
     mha_tc) rx='regex:mha_tc_kernel' ;;
     argmax) rx='regex:argmax_gather' ;;
-    l2_argmin) rx='regex:l2_argmin_tc' ;;
+    l2_argmin) rx='regex:l2_argmin_pair' ;;
     ln_linear) rx='regex:ln_linear' ;;
     conv_out) rx='regex:conv_out_gn' ;;
   esac

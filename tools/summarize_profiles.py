@@ -97,7 +97,7 @@ KEYS += [('sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'XU (MUF
 OPS = [('window_tc', 'window_attn_tc_kernel<32>: 4 clips x 1024 shifted windows of 48 tokens, C=256, 8 heads (core only: HBM-bound, 24 FLOP/B)'),
        ('mha_tc', 'mha_tc_kernel: 4 clips, L=3072, 8 heads x d=64 (flash attention, O / L in TMEM)'),
        ('argmax', 'argmax_gather_kernel: T=49152 rows x 1024 fp32 logits + gather of 512-float codes'),
-       ('l2_argmin', 'l2_argmin_tc_kernel: T=49152 tokens x 1024 codes x 512 (bf16 tensor-core scores + certified window)'),
+       ('l2_argmin', 'l2_argmin_pair_kernel (after z_pack_kernel): T=49152 tokens x 1024 codes x 512, random z (bf16 tensor-core scores on CTA pairs + certified window + exact resolution)'),
        ('ln_linear', 'ln_linear_kernel: LayerNorm + q/kv projection, T=196608, C=256 -> 768'),
        ('conv_out', 'conv_out_gn_kernel: norm_out + SiLU + conv 64->3, 12 frames 512^2, fp32 NCHW output'),
        ('halo64', 'conv_halo_kernel<64>: 3x3, 12 frames 512^2, Cin=Cout=64, residual (weights resident)'),
