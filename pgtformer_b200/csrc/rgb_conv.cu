@@ -3,13 +3,16 @@
 // K = 27 / 147 is far too small for a TMA-fed implicit GEMM (no 16-byte channel vectors to tile), and a patch matrix
 // in HBM costs more than the conv, so the im2col happens inside the kernel:
 //
-//   warps 0..3   builders: thread = one output pixel; gathers its 3 k^2 inputs (coalesced across the warp: lanes are
-//                neighbouring pixels), optional (x - mean) / std, bf16, and writes the row of the 128 x K A tile
-//                straight into the 128B-swizzled K-major layout the UMMA descriptor expects (double buffered)
-//   warp 8       tcgen05.mma issuer: K/16 instructions per tile against the weight tile resident in smem, accumulator
-//                [128 x 64] fp32 in TMEM (double buffered)
-//   warps 4..7   epilogue: TMEM -> bias (+ReLU) -> optional GroupNorm(32) partial statistics -> bf16 -> swizzled
+//   builders     (4 warps for 3x3, 8 for 7x7: two threads share a pixel, each gathers half of its K range): thread = one
+//                output pixel; gathers its 3 k^2 inputs (coalesced across the warp: lanes are neighbouring pixels),
+//                optional (x - mean) / std, bf16, and writes the row of the 128 x K A tile straight into the
+//                128B-swizzled K-major layout the UMMA descriptor expects (double buffered)
+//   next 4 warps epilogue: TMEM -> bias (+ReLU) -> optional GroupNorm(32) partial statistics -> bf16 -> swizzled
 //                staging tile -> one TMA store per tile
+//   last warp    tcgen05.mma issuer: K/16 instructions per tile against the weight tile resident in smem, accumulator
+//                [128 x 64] fp32 in TMEM (double buffered)
+// The 3x3 kernel runs two CTAs per SM (74 KB of shared memory, 128 TMEM columns each): a tile's chain
+// gather -> MMA -> epilogue -> store is latency-bound, a second CTA fills the gaps.
 #include <cudaTypedefs.h>
 
 #include "common.cuh"
@@ -20,7 +23,6 @@
 namespace pgt {
 
 constexpr int RC_N = 64;                 // output channels (both layers)
-constexpr int RC_THREADS = 288;
 constexpr int RC_SUB = 128 * 128;        // [128 rows x 64 k] bf16 A sub-tile
 constexpr int RC_BSUB = RC_N * 128;      // [64 rows x 64 k] bf16 weight sub-tile
 
@@ -44,10 +46,41 @@ struct RgbCfg {
   static constexpr int A_BYTES = NSUB * RC_SUB;
   static constexpr int B_BYTES = NSUB * RC_BSUB;
   static constexpr int SMEM = 2 * A_BYTES + B_BYTES + 2 * RC_SUB /*staging*/ + 256;
+  static constexpr int BW = KS == 3 ? 4 : 8;                    // builder warps
+  static constexpr int PARTS = BW / 4;                          // threads per output pixel
+  static constexpr int THREADS = (BW + 5) * 32;
+  static constexpr int PER_SM = KS == 3 ? 2 : 1;                // resident CTAs per SM
 };
 
+// 16-byte chunks [CH0, CH1) of one A row (one output pixel): every tap offset is a compile-time constant
+template <int KS, int CH0, int CH1>
+__device__ __forceinline__ void rgb_build_chunks(const RgbConvParams& p, const float* x0, size_t plane, int iy0, int ix0, bool valid,
+                                                 uint8_t* arow, int r) {
+  constexpr int K = 3 * KS * KS;
+#pragma unroll
+  for (int ch = CH0; ch < CH1; ++ch) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = ch * 8 + j;
+      if (k < K) {
+        const int tap = k / 3, c = k - tap * 3;
+        const int ky = tap / KS, kx = tap - ky * KS;
+        const bool ok = valid && (unsigned)(iy0 + ky) < (unsigned)p.H && (unsigned)(ix0 + kx) < (unsigned)p.W;
+        v[j] = ok ? (__ldg(x0 + c * plane + ky * p.W + kx) - p.mean[c]) * p.istd[c] : 0.f;
+      } else {
+        v[j] = 0.f;
+      }
+    }
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(arow + (ch >> 3) * RC_SUB + (((ch & 7) ^ (r & 7)) << 4)) = u;
+  }
+}
+
 template <int KS, int STRIDE, int PAD>
-__global__ void __launch_bounds__(RC_THREADS, KS == 3 ? 2 : 1)
+__global__ void __launch_bounds__(RgbCfg<KS>::THREADS, RgbCfg<KS>::PER_SM)
 rgb_conv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const RgbConvParams p) {
   using Cfg = RgbCfg<KS>;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -64,11 +97,12 @@ rgb_conv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 8) {
+  constexpr int BW = Cfg::BW;
+  if (warp == BW + 4) {
     if (lane == 0) {
       tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmO);
       for (int i = 0; i < 2; ++i) {
-        mbar_init(&a_full[i], 128); mbar_init(&a_free[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], 128);
+        mbar_init(&a_full[i], BW * 32); mbar_init(&a_free[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], 128);
       }
       mbar_init(b_full, 1);
       fence_barrier_init();
@@ -83,9 +117,11 @@ rgb_conv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp < 4) {
+  if (warp < BW) {
     // ------------------------------------------------------------------ builders
-    const int r = threadIdx.x;
+    const int r = threadIdx.x & 127;
+    const int part = threadIdx.x >> 7;                  // which share of the row's 16-byte chunks this thread gathers
+    constexpr int CH_PER = (Cfg::NCH + Cfg::PARTS - 1) / Cfg::PARTS;
     const size_t plane = (size_t)p.H * p.W;
     const int HoWo = p.Ho * p.Wo;
     int it = 0;
@@ -100,34 +136,16 @@ rgb_conv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
       const float* x0 = p.x + (size_t)f * 3 * plane + (long long)iy0 * p.W + ix0;
       mbar_wait(&a_free[buf], ((it >> 1) & 1) ^ 1);
       uint8_t* arow = sA + buf * Cfg::A_BYTES + r * 128;
-#pragma unroll
-      for (int ch = 0; ch < Cfg::NCH; ++ch) {
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int k = ch * 8 + j;
-          if (k < Cfg::K) {
-            const int tap = k / 3, c = k - tap * 3;
-            const int ky = tap / KS, kx = tap - ky * KS;
-            const bool ok = valid && (unsigned)(iy0 + ky) < (unsigned)p.H && (unsigned)(ix0 + kx) < (unsigned)p.W;
-            v[j] = ok ? (__ldg(x0 + c * plane + ky * p.W + kx) - p.mean[c]) * p.istd[c] : 0.f;
-          } else {
-            v[j] = 0.f;
-          }
-        }
-        uint4 u;
-        u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
-        u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-        *reinterpret_cast<uint4*>(arow + (ch >> 3) * RC_SUB + (((ch & 7) ^ (r & 7)) << 4)) = u;
-      }
+      if (part == 0) rgb_build_chunks<KS, 0, CH_PER < Cfg::NCH ? CH_PER : Cfg::NCH>(p, x0, plane, iy0, ix0, valid, arow, r);
+      else rgb_build_chunks<KS, CH_PER < Cfg::NCH ? CH_PER : Cfg::NCH, Cfg::NCH>(p, x0, plane, iy0, ix0, valid, arow, r);
       fence_proxy_async();
       mbar_arrive(&a_full[buf]);
     }
-  } else if (warp < 8) {
+  } else if (warp < BW + 4) {
     // ------------------------------------------------------------------ epilogue
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
-    const int et = threadIdx.x - 128;
+    const int et = threadIdx.x - BW * 32;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -206,7 +224,7 @@ rgb_conv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == BW + 4) {
     tc_fence_after();
     tmem_dealloc<128>(tmem_base);
   }
@@ -220,20 +238,18 @@ template <int KS, int STRIDE, int PAD>
 static int launch_rgb(const CUtensorMap& tw, const CUtensorMap& to, const RgbConvParams& p, cudaStream_t st, const char* desc) {
   using Cfg = RgbCfg<KS>;
   static PerDeviceOnce once;
-  static int per_sm = 1;                        // identical on every device of the box (same chip)
   PGT_CUDA_OK(once.run([] {
     cudaError_t e = cudaFuncSetAttribute(rgb_conv_kernel<KS, STRIDE, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return e;
-    int n = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rgb_conv_kernel<KS, STRIDE, PAD>, RC_THREADS, Cfg::SMEM);
-    if (e != cudaSuccess) return e;
-    per_sm = n < 1 ? 1 : (n > 4 ? 4 : n);       // 128 TMEM columns per CTA
-    return cudaSuccess;
+    // the resident-CTA count is fixed by the kernel's own budget (__launch_bounds__, shared memory, 128 TMEM columns), not
+    // asked of the occupancy calculator: it answered 1 for the 3x3 kernel and left half of every SM idle
+    return cudaFuncSetAttribute(rgb_conv_kernel<KS, STRIDE, PAD>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared);
   }));
-  const int grid = p.m_tiles < num_sms() * per_sm ? p.m_tiles : num_sms() * per_sm;
+  const int grid = p.m_tiles < num_sms() * Cfg::PER_SM ? p.m_tiles : num_sms() * Cfg::PER_SM;
   {
     ProfScope ps(PGT_PROF_GEMM, 2.0 * (double)p.M * RC_N * Cfg::K, st, desc);
-    rgb_conv_kernel<KS, STRIDE, PAD><<<grid, RC_THREADS, Cfg::SMEM, st>>>(tw, to, p);
+    rgb_conv_kernel<KS, STRIDE, PAD><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tw, to, p);
   }
   PGT_LAUNCH_OK();
   return PGT_OK;
