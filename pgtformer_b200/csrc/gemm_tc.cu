@@ -153,15 +153,33 @@ struct EpiCtx {
   uint32_t tmem_empty_cluster;   // != 0: shared::cluster address of the pair leader's tmem_empty[0] (2-CTA kernels)
 };
 
-// One 32-column chunk of a staging panel: TMEM -> +bias -> act -> (+residual | SFT) -> packed into the swizzled row.
+// One 32-column chunk of a staging panel, accumulators already in registers (v): +bias -> act -> (+residual | SFT)
+// -> packed into the swizzled staging row.  srow is the SHARED-space address of this thread's 128-byte row: explicit
+// ld.shared / st.shared (generic LD / ST through the shared window cost several times the latency), and the
+// residual vectors are all fetched before the first store so that they overlap instead of serialising behind it.
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 u;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(a) : "memory");
+  return u;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& u) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+
 template <bool kSft>
-__device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, const float* bias32, uint8_t* srow,
-                                          int r, int sub, int esize, bool has_res, float* gq = nullptr, int gcol = 0) {
-  uint32_t v[32];
-  tmem_ld_32x32(taddr, v);
-  tmem_ld_wait();
+__device__ __forceinline__ void epi_finish(const GemmParams& p, const uint32_t (&v)[32], const float* bias32, uint32_t srow,
+                                           int r, int sub, int esize, bool has_res, float* gq, int gcol,
+                                           const float4 (&pre)[8], bool use_pre) {
   float f[32];
-  if (bias32 != nullptr) {                     // same address in every lane: an L1 broadcast read per float4
+  if (use_pre) {                               // bias chunk already in registers (fetched before the barrier waits)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + pre[q].x;
+      f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + pre[q].y;
+      f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + pre[q].z;
+      f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + pre[q].w;
+    }
+  } else if (bias32 != nullptr) {              // same address in every lane: an L1 broadcast read per float4
     const float4* b4 = reinterpret_cast<const float4*>(bias32);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -183,35 +201,47 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, c
   if (p.act != PGT_ACT_NONE && !p.relu_after_res) act_chunk(f, p.act);
   if (esize == 2) {
     // 32 bf16 = 64 B = chunks (sub*4 .. sub*4+3) of the 128 B swizzled row
+    uint32_t off[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int off = ((((sub << 2) + q) ^ (r & 7)) << 4);
-      uint4* dst = reinterpret_cast<uint4*>(srow + off);
-      if (has_res) {
-        const uint4 u = *dst;
-        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-        const float rr[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
-        if (kSft) {
-          const uint4 ux = *reinterpret_cast<const uint4*>(srow + PANEL_BYTES + off);
-          const float2 sa = unpack_bf16x2(ux.x), sb = unpack_bf16x2(ux.y), sc = unpack_bf16x2(ux.z), sd = unpack_bf16x2(ux.w);
+    for (int q = 0; q < 4; ++q) off[q] = srow + ((((sub << 2) + q) ^ (r & 7)) << 4);
+    if (has_res) {
+      uint4 ur[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ur[q] = lds128(off[q]);
+      if (kSft) {
+        uint4 ux[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ux[q] = lds128(off[q] + PANEL_BYTES);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 a = unpack_bf16x2(ur[q].x), b = unpack_bf16x2(ur[q].y), c = unpack_bf16x2(ur[q].z), d = unpack_bf16x2(ur[q].w);
+          const float rr[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+          const float2 sa = unpack_bf16x2(ux[q].x), sb = unpack_bf16x2(ux[q].y), sc = unpack_bf16x2(ux[q].z), sd = unpack_bf16x2(ux[q].w);
           const float ss[8] = {sa.x, sa.y, sb.x, sb.y, sc.x, sc.y, sd.x, sd.y};
 #pragma unroll
           for (int e = 0; e < 8; ++e) f[8 * q + e] = rr[e] + p.sft_w * (rr[e] * ss[e] + f[8 * q + e]);
-        } else {
+        }
+      } else {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[8 * q + e] += rr[e];
+        for (int q = 0; q < 4; ++q) {
+          const float2 a = unpack_bf16x2(ur[q].x), b = unpack_bf16x2(ur[q].y), c = unpack_bf16x2(ur[q].z), d = unpack_bf16x2(ur[q].w);
+          f[8 * q + 0] += a.x; f[8 * q + 1] += a.y; f[8 * q + 2] += b.x; f[8 * q + 3] += b.y;
+          f[8 * q + 4] += c.x; f[8 * q + 5] += c.y; f[8 * q + 6] += d.x; f[8 * q + 7] += d.y;
         }
       }
-      if (p.relu_after_res) {
+    }
+    if (p.relu_after_res) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[8 * q + e] = fmaxf(f[8 * q + e], 0.f);
-      }
+      for (int e = 0; e < 32; ++e) f[e] = fmaxf(f[e], 0.f);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
       uint4 o;
       o.x = pack_bf16x2(f[8 * q + 0], f[8 * q + 1]);
       o.y = pack_bf16x2(f[8 * q + 2], f[8 * q + 3]);
       o.z = pack_bf16x2(f[8 * q + 4], f[8 * q + 5]);
       o.w = pack_bf16x2(f[8 * q + 6], f[8 * q + 7]);
-      *dst = o;
+      sts128(off[q], o);
     }
     if (gq != nullptr) {                       // fused GroupNorm statistics of the (pre-rounding) output values
       const int lane = r & 31;
@@ -225,16 +255,26 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, uint32_t taddr, c
     }
   } else {
     // 32 fp32 = 128 B = the whole swizzled row
+    if (has_res) {
+      uint4 ur[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) ur[q] = lds128(srow + ((q ^ (r & 7)) << 4));
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        f[4 * q + 0] += __uint_as_float(ur[q].x); f[4 * q + 1] += __uint_as_float(ur[q].y);
+        f[4 * q + 2] += __uint_as_float(ur[q].z); f[4 * q + 3] += __uint_as_float(ur[q].w);
+      }
+    }
+    if (p.relu_after_res) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) f[e] = fmaxf(f[e], 0.f);
+    }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      float4* dst = reinterpret_cast<float4*>(srow + ((q ^ (r & 7)) << 4));
-      float4 o = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-      if (has_res) {
-        const float4 u = *dst;
-        o.x += u.x; o.y += u.y; o.z += u.z; o.w += u.w;
-      }
-      if (p.relu_after_res) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-      *dst = o;
+      uint4 o;
+      o.x = __float_as_uint(f[4 * q]); o.y = __float_as_uint(f[4 * q + 1]);
+      o.z = __float_as_uint(f[4 * q + 2]); o.w = __float_as_uint(f[4 * q + 3]);
+      sts128(srow + ((q ^ (r & 7)) << 4), o);
     }
   }
 }
@@ -307,9 +347,11 @@ __device__ __forceinline__ void epilogue_dma_loop(const GemmParams& p, const Epi
     for (int i = 0; i < R && is.valid(cp); ++i) { prepare(cp, i); is.next(cp); }
   }
   __syncwarp();
+  static_assert(NUM_SLOTS == 4, "ring positions are computed with shifts");
+  const int rshift = sft ? 1 : 2;                        // R = 4, or 2 with SFT: no runtime division on this path
   for (int k = 0; is.valid(cs); ++k, is.next(cs)) {
-    const int pos = k % R;
-    mbar_wait(&ctx.slot_ready[pos], (k / R) & 1);       // the 8 epilogue warps have written item k
+    const int pos = k & (R - 1);
+    mbar_wait(&ctx.slot_ready[pos], (k >> rshift) & 1);  // the 8 epilogue warps have written item k
     if (lane == 0) {
       int col, m_blk, n0, y0, x0;
       coords(cs, col, m_blk, n0, y0, x0);
@@ -317,9 +359,12 @@ __device__ __forceinline__ void epilogue_dma_loop(const GemmParams& p, const Epi
       if (p.mode == MODE_LINEAR) tma_store_2d(&tmO, src, col, m_blk * BM);
       else tma_store_4d(&tmO, src, col, x0, y0, n0);
       bulk_commit();
-      if (is.valid(cp)) {                               // the slot is recycled for item k+R once the store has read it
-        bulk_wait_read<0>();
-        prepare(cp, pos);
+      // recycle the slot of the PREVIOUS item (for item k-1+R): its store has had a whole item's time to read the panel,
+      // so this wait returns at once; waiting for the store just committed (wait_group.read 0) would put a TMA store's
+      // issue-to-read latency between consecutive items
+      if (k >= 1 && is.valid(cp)) {
+        bulk_wait_read<1>();
+        prepare(cp, (k - 1) & (R - 1));
         is.next(cp);
       }
     }
@@ -342,8 +387,6 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, const EpiCtx&
   const int PW = is.PW;
   const int nsub = PW / 32;
   const bool sft = (p.epi_mode == PGT_EPI_SFT);
-  const int S = sft ? 2 : 1;
-  const int R = NUM_SLOTS / S;
   const bool bias_vec = p.bias != nullptr && (p.N % 32) == 0;   // whole chunks inside N: 128-bit bias reads
 
   int k = 0;                                 // item counter
@@ -362,25 +405,54 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, const EpiCtx&
 
     if (p.fast_epi) {
       const int npan = is.panels_in_tile(tile);
-      for (int pnl = 0; pnl < npan; ++pnl, ++k) {
-        const int pos = k % R;
-        mbar_wait(&ctx.res_bar[pos], (k / R) & 1);      // slot free (and residual / scale panel landed)
-        uint8_t* srow = ctx.staging + pos * S * PANEL_BYTES + r * 128;
-        const int pcol = pnl * PW;
-        for (int sub = half; sub < nsub; sub += 2) {
-          const int col0 = col_base + pcol + sub * 32;
-          const float* b32 = bias_vec ? p.bias + col0 : nullptr;
-          float* gq = nullptr;
-          if (p.gn_stats != nullptr) {
-            const size_t chunk = p.gn_tpf > 0 ? (size_t)(m_blk / p.gn_tpf) * p.gn_fstride + (m_blk % p.gn_tpf) * 4 + quad
-                                              : (size_t)m_blk * 4 + quad;
-            gq = p.gn_stats + (chunk * 32 + col0 / p.gn_cpg) * 2;
-          }
-          if (sft) epi_chunk<true>(p, t_row + pcol + sub * 32, b32, srow, r, sub, esize, true, gq, col0);
-          else epi_chunk<false>(p, t_row + pcol + sub * 32, b32, srow, r, sub, esize, p.has_res_map != 0, gq, col0);
+      const uint32_t stg = smem_u32(ctx.staging) + r * 128;
+      auto gn_ptr = [&](int col0) -> float* {
+        if (p.gn_stats == nullptr) return nullptr;
+        const size_t chunk = p.gn_tpf > 0 ? (size_t)(m_blk / p.gn_tpf) * p.gn_fstride + (m_blk % p.gn_tpf) * 4 + quad
+                                          : (size_t)m_blk * 4 + quad;
+        return p.gn_stats + (chunk * 32 + col0 / p.gn_cpg) * 2;
+      };
+      if (sft) {
+        // SFT items take two slots (residual / out + scale): ring of 2, one item at a time
+        for (int pnl = 0; pnl < npan; ++pnl, ++k) {
+          const int pos = k & 1;
+          mbar_wait(&ctx.res_bar[pos], (k >> 1) & 1);     // slot free, residual and scale panels landed
+          const int col0 = col_base + pnl * PW + half * 32;
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + pnl * PW + half * 32, v);
+          tmem_ld_wait();
+          float4 nb[8];
+          epi_finish<true>(p, v, bias_vec ? p.bias + col0 : nullptr, stg + pos * 2 * PANEL_BYTES, r, half, esize, true,
+                           gn_ptr(col0), col0, nb, false);
+          fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA engine
+          mbar_arrive(&ctx.slot_ready[pos]);
         }
-        fence_proxy_async();                 // generic smem writes -> visible to the TMA engine
-        mbar_arrive(&ctx.slot_ready[pos]);
+      } else {
+        // One item (panel) at a time; bf16 (two 32-column chunks per panel): the quadrant's two warps take one chunk each,
+        // fp32 (one chunk per panel): they take alternate panels.  The bias chunk is fetched BEFORE the slot wait and the
+        // TMEM read: under a shared-memory / L1 data pipe saturated by MMA operand reads and TMA fills an L1-hit load
+        // takes several hundred cycles, which those waits then cover.
+        for (int pnl = 0; pnl < npan; ++pnl, ++k) {
+          const int pos = k & 3;
+          const bool mine = (nsub == 2) || ((pnl & 1) == half);
+          const int sb = (nsub == 2) ? half : 0;
+          const int col0 = col_base + pnl * PW + sb * 32;
+          float4 b[8];
+          if (mine && bias_vec) {
+            const float4* g = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) b[q] = __ldg(g + q);
+          }
+          mbar_wait(&ctx.res_bar[pos], (k >> 2) & 1);      // slot free (and residual panel landed)
+          if (mine) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_row + pnl * PW + sb * 32, v);
+            tmem_ld_wait();
+            epi_finish<false>(p, v, nullptr, stg + pos * PANEL_BYTES, r, sb, esize, p.has_res_map != 0, gn_ptr(col0), col0, b, bias_vec);
+          }
+          fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA engine
+          mbar_arrive(&ctx.slot_ready[pos]);
+        }
       }
     } else {
       // ---------------- direct path (NCHW fp32 output, unaligned views, mixed residual dtype): per-thread global I/O

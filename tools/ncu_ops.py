@@ -44,6 +44,24 @@ elif which == 'linear256':
     out = torch.empty(M, 256, device=dev, dtype=torch.bfloat16)
     for _ in range(3):
         ops.linear(a, w, out, bias=b, residual=res)
+elif which in ('linear512', 'linear512_f32'):
+    # the 32^2-level Swin / global-transformer linears: M = 49152 tokens, N = K = 512 (bf16 or fp32 residual stream)
+    M = 49152
+    dt = torch.float32 if which.endswith('f32') else torch.bfloat16
+    a = torch.randn(M, 512, device=dev).bfloat16()
+    w = (torch.randn(512, 512, device=dev) * 0.05).bfloat16()
+    b = torch.zeros(512, device=dev)
+    res = torch.randn(M, 512, device=dev).to(dt)
+    out = torch.empty(M, 512, device=dev, dtype=dt)
+    for _ in range(3):
+        ops.linear(a, w, out, bias=b, residual=res)
+elif which == 'up128':
+    from pgtformer_b200.engine import _pack_up2x
+    x = torch.randn(F, 256, 256, 128, device=dev).bfloat16()
+    w = _pack_up2x(torch.randn(128, 128, 3, 3, device=dev) * 0.05)
+    out = torch.empty(F, 512, 512, 128, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.conv_up2x(x, w, 128, out, bias=torch.zeros(128, device=dev))
 elif which == 'swin_mlp':
     M = 786432 // 4
     x = torch.randn(M, 256, device=dev).bfloat16()
