@@ -4,13 +4,20 @@
 // memory in place, and the same tile is the A operand of all N / 256 column blocks.
 //
 // Per CTA, persistent over 128-token tiles (352 threads):
-//   warp 0      TMA producer of the weight k-blocks ([256 x 64] each, 3-deep ring; N/256 x 4 per tile)
+//   warp 0      TMA producer of the weight k-blocks ([256 x 64] each, 2-deep ring; N/256 x 4 per tile)
 //   warp 1      tcgen05.mma issuer: column block j accumulates in TMEM columns [256 (j & 1), +256) — the epilogue of
 //               block j overlaps the MMAs of block j + 1
-//   warps 2..9  compute: LayerNorm of the x tile in place (two threads per row), then per column block the epilogue
-//               acc + bias -> bf16 -> swizzled staging tile
-//   warp 10     DMA: TMA load of the x tile (as soon as the last MMA of the previous tile has consumed the buffer),
-//               TMA store of each finished [128 x 256] block
+//   warps 2..9  compute: LayerNorm of the NEXT x tile in place (two threads per row) between the epilogues of the
+//               current tile's column blocks (acc + bias -> bf16 -> swizzled 64-column staging panel)
+//   warp 10     DMA: TMA load of x tiles into the buffer the MMAs of two tiles ago have released, TMA store of each
+//               finished [128 x 64] panel
+//
+// Two x buffers (round 2, second pass).  A device timeline of the single-buffer version (clock64 stamps, T = 786432):
+// per 22.4 k-cycle tile the tensor pipe was busy 8.1 k — the x load could only be issued once the tile's last MMA had
+// retired and then took 8.5 k cycles (it queues behind the output stores every CTA has just issued), LayerNorm another
+// 4.4 k, all of it serial.  With x(i+1) loaded and normalised while tile i is multiplied, the tile is bounded by the
+// compute warps (LayerNorm + three epilogues); the shared memory comes from the staging buffer (two 64-column panels
+// instead of two 128-column halves) and the weight ring (2 x 32 KB: the MMAs no longer wait on it first).
 #include <cudaTypedefs.h>
 
 #include <cstdio>
@@ -24,10 +31,11 @@ namespace pgt {
 constexpr int LL_C = 256;
 constexpr int LL_BM = 128;
 constexpr int LL_SUB = LL_BM * 128;            // one [128 x 64] bf16 sub-tile: 16 KB
-constexpr int LL_WST = 3;                      // weight ring depth
+constexpr int LL_WST = 2;                      // weight ring depth
 constexpr int LL_WBYTES = LL_C * 128;          // one [256 x 64] weight k-block: 32 KB
 constexpr int LL_THREADS = 352;
-constexpr int LL_SMEM = 4 * LL_SUB /*x / A*/ + 4 * LL_SUB /*staging*/ + LL_WST * LL_WBYTES + 128 * 8 /*xch*/ + 256;
+constexpr int LL_SMEM = 8 * LL_SUB /*two x / A tiles*/ + 2 * LL_SUB /*staging panels*/ + LL_WST * LL_WBYTES + 128 * 8 /*xch*/ + 256;
+static_assert(LL_SMEM <= 232448, "ln_linear smem budget");
 
 struct LnLinearParams {
   int T, m_tiles, nb;   // nb = N / 256 column blocks
@@ -42,28 +50,30 @@ ln_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmW, const LnLinearParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];     // no static smem in this kernel: the window starts 1024-aligned
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* sX = smem;                           // x tile -> LN(x): the A operand of every column block
-  uint8_t* sO = sX + 4 * LL_SUB;                // finished [128 x 256] block, 4 swizzled sub-tiles
-  uint8_t* sW = sO + 4 * LL_SUB;                // weight ring
+  uint8_t* sX = smem;                           // [2] x tile -> LN(x): the A operand of every column block
+  uint8_t* sO = sX + 8 * LL_SUB;                // [2] finished [128 x 64] panels (ping-pong)
+  uint8_t* sW = sO + 2 * LL_SUB;                // weight ring
   float2* xch = reinterpret_cast<float2*>(sW + LL_WST * LL_WBYTES);     // [128 rows] (sum, sumsq) exchange
   uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 128);
-  uint64_t* x_full = bars;           // DMA -> compute
-  uint64_t* sx_free = bars + 1;      // MMA commit (last column block) -> DMA
-  uint64_t* y_ready = bars + 2;      // compute (256) -> MMA
-  uint64_t* acc_full = bars + 3;     // [2] MMA commit -> compute
-  uint64_t* acc_free = bars + 5;     // [2] compute (256) -> MMA
-  uint64_t* so_free = bars + 7;      // [2] DMA (store has read staging half h) -> compute
-  uint64_t* out_ready = bars + 9;    // [2] compute (256) -> DMA
-  uint64_t* w_full = bars + 11;      // [LL_WST]
+  uint64_t* x_full = bars;           // [2] DMA -> compute
+  uint64_t* sx_free = bars + 2;      // [2] MMA commit (last column block of the tile in that buffer) -> DMA
+  uint64_t* y_ready = bars + 4;      // [2] compute (256) -> MMA
+  uint64_t* acc_full = bars + 6;     // [2] MMA commit -> compute
+  uint64_t* acc_free = bars + 8;     // [2] compute (256) -> MMA
+  uint64_t* so_free = bars + 10;     // [2] DMA (store has read staging panel s) -> compute
+  uint64_t* out_ready = bars + 12;   // [2] compute (256) -> DMA
+  uint64_t* w_full = bars + 14;      // [LL_WST]
   uint64_t* w_empty = w_full + LL_WST;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_empty + LL_WST);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmO); tma_prefetch_desc(&tmW);
-    mbar_init(x_full, 1); mbar_init(sx_free, 1); mbar_init(y_ready, 256);
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], 256); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&so_free[i], 1); mbar_init(&out_ready[i], 256); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&x_full[i], 1); mbar_init(&sx_free[i], 1); mbar_init(&y_ready[i], 256);
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], 256);
+      mbar_init(&so_free[i], 1); mbar_init(&out_ready[i], 256);
+    }
     for (int i = 0; i < LL_WST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     fence_barrier_init();
   }
@@ -100,12 +110,13 @@ ln_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     uint32_t ph = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
-      mbar_wait(y_ready, it & 1);
+      const int xb = it & 1;
+      mbar_wait(&y_ready[xb], (it >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {
         int s = st;
         uint32_t sp = ph;
-        const uint64_t da0 = umma_desc_k_sw128(smem_u32(sX));
+        const uint64_t da0 = umma_desc_k_sw128(smem_u32(sX + xb * 4 * LL_SUB));
         const uint64_t db0 = umma_desc_k_sw128(smem_u32(sW));
         for (int j = 0; j < NB; ++j) {
           const int g = it * NB + j;
@@ -123,7 +134,7 @@ ln_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           }
           umma_commit(&acc_full[g & 1]);
         }
-        umma_commit(sx_free);                       // every MMA that reads the x tile has retired
+        umma_commit(&sx_free[xb]);                  // every MMA that reads this x buffer has retired
       }
       __syncwarp();
       const int ns = st + 4 * NB;
@@ -133,16 +144,16 @@ ln_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   } else if (warp < 10) {
     // ------------------------------------------------------------------ compute warps
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;                    // which 128-column half of the row this thread owns
+    const int half = (warp - 2) >> 2;                    // LN: which 128-column half of the row; epilogue: which chunk of a panel
     const int r = quad * 32 + lane;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
-      // ---- LayerNorm(x) in place (two threads per row; the halves meet through smem)
-      mbar_wait(x_full, it & 1);
+    // LayerNorm of tile number `t` of this CTA, in place in x buffer t & 1 (two threads per row; the halves meet through smem)
+    auto layer_norm = [&](int t) {
+      uint8_t* xb = sX + (t & 1) * 4 * LL_SUB;
+      mbar_wait(&x_full[t & 1], (t >> 1) & 1);
       float s = 0.f, q = 0.f;
 #pragma unroll
       for (int sub = 0; sub < 2; ++sub) {
-        const uint8_t* src = sX + (half * 2 + sub) * LL_SUB + r * 128;
+        const uint8_t* src = xb + (half * 2 + sub) * LL_SUB + r * 128;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const uint4 u = *reinterpret_cast<const uint4*>(src + ((c ^ (r & 7)) << 4));
@@ -170,7 +181,7 @@ ln_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
       for (int sub = 0; sub < 2; ++sub) {
         const int kb = half * 2 + sub;
-        uint8_t* row = sX + kb * LL_SUB + r * 128;
+        uint8_t* row = xb + kb * LL_SUB + r * 128;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           uint4* ptr = reinterpret_cast<uint4*>(row + ((c ^ (r & 7)) << 4));
@@ -192,83 +203,99 @@ ln_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
       }
       fence_proxy_async();
-      mbar_arrive(y_ready);
-      // ---- per column block: acc + bias -> bf16 -> staging tile
+      mbar_arrive(&y_ready[t & 1]);
+      // the xch rows are rewritten by the next LayerNorm: every thread has read its row by now (second barrier above)
+    };
+    if ((int)blockIdx.x < p.m_tiles) layer_norm(0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+      const bool has_next = tile + (int)gridDim.x < p.m_tiles;
+      // ---- per column block: acc + bias -> bf16 -> 64-column staging panels (ping-pong)
       for (int j = 0; j < NB; ++j) {
+        // the next tile is normalised before the last column block's epilogue: its load (issued when the previous tile's
+        // MMAs released the buffer) has had most of a tile's time to land, and MMA(i + 1) needs it only after MMA(i)
+        if (j == NB - 1 && has_next) layer_norm(it + 1);
         const int g = it * NB + j;
         const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + (g & 1) * LL_C;
         mbar_wait(&acc_full[g & 1], (g >> 1) & 1);
         tc_fence_after();
-        // the [128 x 256] block leaves in two 128-column halves through a ping-pong pair of 32 KB staging buffers:
-        // the TMA store of one half reads its buffer while the warps fill the other
 #pragma unroll 1
-        for (int hp = 0; hp < 2; ++hp) {
-          mbar_wait(&so_free[hp], (g & 1) ^ 1);         // the store that last used this half has read it
-#pragma unroll 1
-          for (int cc = 0; cc < 2; ++cc) {
-            const int c0 = hp * 128 + half * 64 + cc * 32;
-            uint32_t v[32];
-            tmem_ld_32x32(t_row + c0, v);
-            tmem_ld_wait();
-            if (hp == 1 && cc == 1) {                    // last TMEM read of this thread: the accumulator may be reused
-              tc_fence_before();
-              mbar_arrive(&acc_free[g & 1]);
-            }
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + j * LL_C + c0);
-            uint8_t* dst = sO + (c0 >> 6) * LL_SUB + r * 128;
-            const int ch0 = (c0 & 63) >> 3;
+        for (int pp = 0; pp < 4; ++pp) {
+          const int n = g * 4 + pp;                    // running panel number: staging buffer n & 1, its (n >> 1)-th use
+          const int sb = n & 1;
+          const int c0 = pp * 64 + half * 32;
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + j * LL_C + c0);
+          float4 bv[8];                                // requested before the waits: L1-hit loads are slow under MMA load
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 ba = __ldg(b4 + 2 * i), bb = __ldg(b4 + 2 * i + 1);
-              uint4 o;
-              o.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) + ba.x, __uint_as_float(v[8 * i + 1]) + ba.y);
-              o.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) + ba.z, __uint_as_float(v[8 * i + 3]) + ba.w);
-              o.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) + bb.x, __uint_as_float(v[8 * i + 5]) + bb.y);
-              o.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) + bb.z, __uint_as_float(v[8 * i + 7]) + bb.w);
-              *reinterpret_cast<uint4*>(dst + (((ch0 + i) ^ (r & 7)) << 4)) = o;
-            }
+          for (int i = 0; i < 8; ++i) bv[i] = __ldg(b4 + i);
+          mbar_wait(&so_free[sb], ((n >> 1) & 1) ^ 1);   // the store that last used this panel has read it
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + c0, v);
+          tmem_ld_wait();
+          if (pp == 3) {                               // last TMEM read of this thread: the accumulator may be reused
+            tc_fence_before();
+            mbar_arrive(&acc_free[g & 1]);
+          }
+          const uint32_t dst = smem_u32(sO) + sb * LL_SUB + r * 128;
+          const int ch0 = half * 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 ba = bv[2 * i], bb = bv[2 * i + 1];
+            const uint32_t ox = pack_bf16x2(__uint_as_float(v[8 * i + 0]) + ba.x, __uint_as_float(v[8 * i + 1]) + ba.y);
+            const uint32_t oy = pack_bf16x2(__uint_as_float(v[8 * i + 2]) + ba.z, __uint_as_float(v[8 * i + 3]) + ba.w);
+            const uint32_t oz = pack_bf16x2(__uint_as_float(v[8 * i + 4]) + bb.x, __uint_as_float(v[8 * i + 5]) + bb.y);
+            const uint32_t ow = pack_bf16x2(__uint_as_float(v[8 * i + 6]) + bb.z, __uint_as_float(v[8 * i + 7]) + bb.w);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((ch0 + i) ^ (r & 7)) << 4)), "r"(ox), "r"(oy),
+                         "r"(oz), "r"(ow) : "memory");
           }
           fence_proxy_async();
-          mbar_arrive(&out_ready[hp]);
+          mbar_arrive(&out_ready[sb]);
         }
       }
     }
   } else {
     // ------------------------------------------------------------------ DMA warp
     int it = 0;
-    int pending = -1;                                  // staging half of the newest committed store (not yet released)
-    if (lane == 0 && (int)blockIdx.x < p.m_tiles) {
-      mbar_arrive_expect_tx(x_full, 4 * LL_SUB);
-      for (int kb = 0; kb < 4; ++kb) tma_load_2d(sX + kb * LL_SUB, &tmX, x_full, kb * 64, blockIdx.x * LL_BM);
+    int pending = -1;                                  // staging panel of the newest committed store (not yet released)
+    if (lane == 0) {
+      for (int t = 0; t < 2; ++t) {
+        const int tile = blockIdx.x + t * gridDim.x;
+        if (tile < p.m_tiles) {
+          mbar_arrive_expect_tx(&x_full[t], 4 * LL_SUB);
+          for (int kb = 0; kb < 4; ++kb) tma_load_2d(sX + (t * 4 + kb) * LL_SUB, &tmX, &x_full[t], kb * 64, tile * LL_BM);
+        }
+      }
     }
     __syncwarp();
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+      const int xb = it & 1;
       for (int j = 0; j < NB; ++j) {
         const int g = it * NB + j;
         if (j == NB - 1) {
-          // the x buffer is free once the last column block's MMAs have retired: fetch the next tile now
-          const int nt = tile + gridDim.x;
+          // this tile's x buffer is free once its last column block's MMAs have retired: fetch the tile after next
+          const int nt = tile + 2 * gridDim.x;
           if (nt < p.m_tiles) {
-            mbar_wait(sx_free, it & 1);
+            mbar_wait(&sx_free[xb], (it >> 1) & 1);
             if (lane == 0) {
-              mbar_arrive_expect_tx(x_full, 4 * LL_SUB);
-              for (int kb = 0; kb < 4; ++kb) tma_load_2d(sX + kb * LL_SUB, &tmX, x_full, kb * 64, nt * LL_BM);
+              mbar_arrive_expect_tx(&x_full[xb], 4 * LL_SUB);
+              for (int kb = 0; kb < 4; ++kb) tma_load_2d(sX + (xb * 4 + kb) * LL_SUB, &tmX, &x_full[xb], kb * 64, nt * LL_BM);
             }
             __syncwarp();
           }
         }
-        for (int hp = 0; hp < 2; ++hp) {
-          mbar_wait(&out_ready[hp], g & 1);
+        for (int pp = 0; pp < 4; ++pp) {
+          const int n = g * 4 + pp;
+          const int sb = n & 1;
+          mbar_wait(&out_ready[sb], (n >> 1) & 1);
           if (lane == 0) {
-            for (int q = 0; q < 2; ++q)
-              tma_store_2d(&tmO, sO + (2 * hp + q) * LL_SUB, j * LL_C + hp * 128 + q * 64, tile * LL_BM);
+            tma_store_2d(&tmO, sO + sb * LL_SUB, j * LL_C + pp * 64, tile * LL_BM);
             bulk_commit();
             if (pending >= 0) {
-              bulk_wait_read<1>();                       // the store before this one has read its half
+              bulk_wait_read<1>();                       // the store before this one has read its panel
               mbar_arrive(&so_free[pending]);
             }
           }
-          pending = hp;
+          pending = sb;
           __syncwarp();
         }
       }
