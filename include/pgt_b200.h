@@ -177,7 +177,9 @@ int pgt_layernorm(const void* x, int ldx, int x_dtype, int T, int C, const float
 
 /* ---- LayerNorm fused into the GEMM that consumes it (C = 256, N % 256 == 0):  out[T, N] = LN(x) W^T + bias in ONE kernel —
  * the normalised token matrix never reaches HBM.  W: bf16 [N, ldw] row-major ([out, in]).  Returns PGT_ERR_UNSUPPORTED
- * otherwise.  Replaces norm1 + the q / kv projections of VSTSREncoderTransformerBlock / WindowAttention3D
+ * otherwise.  ln_g == ln_b == NULL: plain normalisation (x - mean) * rstd — the caller has folded gamma / beta into
+ * W and bias (W * gamma along the input dim, bias + W beta), which spares the kernel 2 x 256 parameter reads per row.
+ * Replaces norm1 + the q / kv projections of VSTSREncoderTransformerBlock / WindowAttention3D
  * (modules/rstt_layers.py:116-132,176-188,326-330). */
 int pgt_ln_linear_bf16(const void* x, int ldx, int T, int C, const float* ln_g, const float* ln_b, float eps,
                        const void* W, int ldw, int N, const float* bias, void* out, int ldo, void* stream);

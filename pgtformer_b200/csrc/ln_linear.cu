@@ -7,17 +7,18 @@
 //   warp 0      TMA producer of the weight k-blocks ([256 x 64] each, 2-deep ring; N/256 x 4 per tile)
 //   warp 1      tcgen05.mma issuer: column block j accumulates in TMEM columns [256 (j & 1), +256) — the epilogue of
 //               block j overlaps the MMAs of block j + 1
-//   warps 2..9  compute: LayerNorm of the NEXT x tile in place (two threads per row) between the epilogues of the
-//               current tile's column blocks (acc + bias -> bf16 -> swizzled 64-column staging panel)
+//   warps 2..9  epilogue of the column blocks: acc + bias -> bf16 -> swizzled 64-column staging panel
 //   warp 10     DMA: TMA load of x tiles into the buffer the MMAs of two tiles ago have released, TMA store of each
 //               finished [128 x 64] panel
+//   warps 11..14 LayerNorm of the NEXT x tile in place, one thread per row (no cross-thread exchange), concurrent with
+//               the epilogues and MMAs of the current tile
 //
 // Two x buffers (round 2, second pass).  A device timeline of the single-buffer version (clock64 stamps, T = 786432):
 // per 22.4 k-cycle tile the tensor pipe was busy 8.1 k — the x load could only be issued once the tile's last MMA had
 // retired and then took 8.5 k cycles (it queues behind the output stores every CTA has just issued), LayerNorm another
-// 4.4 k, all of it serial.  With x(i+1) loaded and normalised while tile i is multiplied, the tile is bounded by the
-// compute warps (LayerNorm + three epilogues); the shared memory comes from the staging buffer (two 64-column panels
-// instead of two 128-column halves) and the weight ring (2 x 32 KB: the MMAs no longer wait on it first).
+// 4.4 k, all of it serial.  Now x(i+1) is loaded and normalised (by warps of its own: with the LayerNorm on the epilogue
+// warps the tile was still bounded by LayerNorm + three epilogues, 16.7 k) while tile i is multiplied; the shared memory
+// comes from the staging buffer (two 64-column panels instead of two 128-column halves) and the weight ring (2 x 32 KB).
 #include <cudaTypedefs.h>
 
 #include <cstdio>
@@ -33,8 +34,8 @@ constexpr int LL_BM = 128;
 constexpr int LL_SUB = LL_BM * 128;            // one [128 x 64] bf16 sub-tile: 16 KB
 constexpr int LL_WST = 2;                      // weight ring depth
 constexpr int LL_WBYTES = LL_C * 128;          // one [256 x 64] weight k-block: 32 KB
-constexpr int LL_THREADS = 352;
-constexpr int LL_SMEM = 8 * LL_SUB /*two x / A tiles*/ + 2 * LL_SUB /*staging panels*/ + LL_WST * LL_WBYTES + 128 * 8 /*xch*/ + 256;
+constexpr int LL_THREADS = 480;
+constexpr int LL_SMEM = 8 * LL_SUB /*two x / A tiles*/ + 2 * LL_SUB /*staging panels*/ + LL_WST * LL_WBYTES + 256;
 static_assert(LL_SMEM <= 232448, "ln_linear smem budget");
 
 struct LnLinearParams {
@@ -53,11 +54,10 @@ ln_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint8_t* sX = smem;                           // [2] x tile -> LN(x): the A operand of every column block
   uint8_t* sO = sX + 8 * LL_SUB;                // [2] finished [128 x 64] panels (ping-pong)
   uint8_t* sW = sO + 2 * LL_SUB;                // weight ring
-  float2* xch = reinterpret_cast<float2*>(sW + LL_WST * LL_WBYTES);     // [128 rows] (sum, sumsq) exchange
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 128);
-  uint64_t* x_full = bars;           // [2] DMA -> compute
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + LL_WST * LL_WBYTES);
+  uint64_t* x_full = bars;           // [2] DMA -> LayerNorm warps
   uint64_t* sx_free = bars + 2;      // [2] MMA commit (last column block of the tile in that buffer) -> DMA
-  uint64_t* y_ready = bars + 4;      // [2] compute (256) -> MMA
+  uint64_t* y_ready = bars + 4;      // [2] LayerNorm warps (128) -> MMA
   uint64_t* acc_full = bars + 6;     // [2] MMA commit -> compute
   uint64_t* acc_free = bars + 8;     // [2] compute (256) -> MMA
   uint64_t* so_free = bars + 10;     // [2] DMA (store has read staging panel s) -> compute
@@ -70,7 +70,7 @@ ln_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmO); tma_prefetch_desc(&tmW);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&x_full[i], 1); mbar_init(&sx_free[i], 1); mbar_init(&y_ready[i], 256);
+      mbar_init(&x_full[i], 1); mbar_init(&sx_free[i], 1); mbar_init(&y_ready[i], 128);
       mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], 256);
       mbar_init(&so_free[i], 1); mbar_init(&out_ready[i], 256);
     }
@@ -144,77 +144,12 @@ ln_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   } else if (warp < 10) {
     // ------------------------------------------------------------------ compute warps
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;                    // LN: which 128-column half of the row; epilogue: which chunk of a panel
+    const int half = (warp - 2) >> 2;                    // which 32-column chunk of a 64-column panel
     const int r = quad * 32 + lane;
-    // LayerNorm of tile number `t` of this CTA, in place in x buffer t & 1 (two threads per row; the halves meet through smem)
-    auto layer_norm = [&](int t) {
-      uint8_t* xb = sX + (t & 1) * 4 * LL_SUB;
-      mbar_wait(&x_full[t & 1], (t >> 1) & 1);
-      float s = 0.f, q = 0.f;
-#pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
-        const uint8_t* src = xb + (half * 2 + sub) * LL_SUB + r * 128;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 u = *reinterpret_cast<const uint4*>(src + ((c ^ (r & 7)) << 4));
-          const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-          s += (a.x + a.y) + (b.x + b.y) + (cc.x + cc.y) + (d.x + d.y);
-          q += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + cc.x * cc.x + cc.y * cc.y + d.x * d.x + d.y * d.y;
-        }
-      }
-      if (half == 0) xch[r] = make_float2(s, q);
-      named_bar_sync(5, 256);
-      if (half == 1) {
-        const float2 o = xch[r];
-        s += o.x; q += o.y;
-        xch[r] = make_float2(s, q);
-      }
-      named_bar_sync(5, 256);
-      if (half == 0) {
-        const float2 o = xch[r];
-        s = o.x; q = o.y;
-      }
-      const float mean = s * (1.f / LL_C);
-      const float var = fmaxf(q * (1.f / LL_C) - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + p.eps);
-      const float nm = -mean * rstd;
-#pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
-        const int kb = half * 2 + sub;
-        uint8_t* row = xb + kb * LL_SUB + r * 128;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint4* ptr = reinterpret_cast<uint4*>(row + ((c ^ (r & 7)) << 4));
-          const uint4 u = *ptr;
-          const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-          const float v[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
-          const int col = kb * 64 + c * 8;
-          const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_g + col)), g1 = __ldg(reinterpret_cast<const float4*>(p.ln_g + col + 4));
-          const float4 e0 = __ldg(reinterpret_cast<const float4*>(p.ln_b + col)), e1 = __ldg(reinterpret_cast<const float4*>(p.ln_b + col + 4));
-          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-          const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-          float y[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) y[j] = fmaf(fmaf(v[j], rstd, nm), gg[j], ee[j]);
-          uint4 o;
-          o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
-          o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
-          *ptr = o;
-        }
-      }
-      fence_proxy_async();
-      mbar_arrive(&y_ready[t & 1]);
-      // the xch rows are rewritten by the next LayerNorm: every thread has read its row by now (second barrier above)
-    };
-    if ((int)blockIdx.x < p.m_tiles) layer_norm(0);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
-      const bool has_next = tile + (int)gridDim.x < p.m_tiles;
       // ---- per column block: acc + bias -> bf16 -> 64-column staging panels (ping-pong)
       for (int j = 0; j < NB; ++j) {
-        // the next tile is normalised before the last column block's epilogue: its load (issued when the previous tile's
-        // MMAs released the buffer) has had most of a tile's time to land, and MMA(i + 1) needs it only after MMA(i)
-        if (j == NB - 1 && has_next) layer_norm(it + 1);
         const int g = it * NB + j;
         const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + (g & 1) * LL_C;
         mbar_wait(&acc_full[g & 1], (g >> 1) & 1);
@@ -253,7 +188,7 @@ ln_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
       }
     }
-  } else {
+  } else if (warp == 10) {
     // ------------------------------------------------------------------ DMA warp
     int it = 0;
     int pending = -1;                                  // staging panel of the newest committed store (not yet released)
@@ -301,6 +236,60 @@ ln_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
     }
     if (lane == 0) bulk_wait0();
+  } else {
+    // ------------------------------------------------------------------ LayerNorm warps (11..14): thread = row
+    const int r = (warp - 11) * 32 + lane;
+    const bool affine = p.ln_g != nullptr;             // nullptr: gamma / beta folded into W / bias by the caller
+    int t = 0;
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++t) {
+      const uint32_t xb = smem_u32(sX) + (t & 1) * 4 * LL_SUB + r * 128;
+      mbar_wait(&x_full[t & 1], (t >> 1) & 1);
+      float s = 0.f, q = 0.f;
+#pragma unroll
+      for (int sub = 0; sub < 4; ++sub) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 u;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                       : "r"(xb + sub * LL_SUB + ((c ^ (r & 7)) << 4)) : "memory");
+          const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+          s += (a.x + a.y) + (b.x + b.y) + (cc.x + cc.y) + (d.x + d.y);
+          q += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + cc.x * cc.x + cc.y * cc.y + d.x * d.x + d.y * d.y;
+        }
+      }
+      const float mean = s * (1.f / LL_C);
+      const float var = fmaxf(q * (1.f / LL_C) - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + p.eps);
+      const float nm = -mean * rstd;
+#pragma unroll 1
+      for (int sub = 0; sub < 4; ++sub) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t addr = xb + sub * LL_SUB + ((c ^ (r & 7)) << 4);
+          uint4 u;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr) : "memory");
+          const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+          const float v[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
+          float y[8];
+          if (affine) {
+            const int col = sub * 64 + c * 8;
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_g + col)), g1 = __ldg(reinterpret_cast<const float4*>(p.ln_g + col + 4));
+            const float4 e0 = __ldg(reinterpret_cast<const float4*>(p.ln_b + col)), e1 = __ldg(reinterpret_cast<const float4*>(p.ln_b + col + 4));
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = fmaf(fmaf(v[j], rstd, nm), gg[j], ee[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = fmaf(v[j], rstd, nm);
+          }
+          const uint32_t ox = pack_bf16x2(y[0], y[1]), oy = pack_bf16x2(y[2], y[3]), oz = pack_bf16x2(y[4], y[5]), ow = pack_bf16x2(y[6], y[7]);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(ox), "r"(oy), "r"(oz), "r"(ow) : "memory");
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&y_ready[t & 1]);
+    }
   }
 
   tc_fence_before();
@@ -321,7 +310,7 @@ using namespace pgt;
 
 extern "C" int pgt_ln_linear_bf16(const void* x, int ldx, int T, int C, const float* ln_g, const float* ln_b, float eps,
                                   const void* W, int ldw, int N, const float* bias, void* out, int ldo, void* stream) {
-  PGT_CHECK_ARG(x && out && ln_g && ln_b && W && bias && T > 0 && N > 0);
+  PGT_CHECK_ARG(x && out && W && bias && T > 0 && N > 0 && ((ln_g == nullptr) == (ln_b == nullptr)));   // both null: no affine
   if (C != LL_C || (N % LL_C) != 0) return PGT_ERR_UNSUPPORTED;
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   PGT_CHECK_ARG(al(x) && al(out) && al(W) && ldx % 8 == 0 && ldo % 8 == 0 && ldw % 8 == 0 && ldw >= C && ldo >= N);

@@ -123,6 +123,14 @@ class Engine:
                 w[p + '.tab16'] = ops.window_tables(w[p + '.bias_tab'])     # tcgen05 window kernel: bias + mask, 4 box layouts
                 w[p + '.qkv.weight'] = _pack_lin(torch.cat([sd[p + '.q.weight'], sd[p + '.kv.weight']], 0).float())
                 w[p + '.qkv.bias'] = torch.cat([sd[p + '.q.bias'], sd[p + '.kv.bias']], 0).float().contiguous()
+                blk = p[:-len('.attn')]
+                if self.fuse_ln_qkv and sd[p + '.q.weight'].shape[1] == 256 and (blk + '.norm1.weight') in sd:
+                    # norm1's affine folded into the projection the fused kernel applies to the normalised tile:
+                    # (xh * g + b) W^T + c = xh (W * g)^T + (W b + c); products and sums in fp32, one bf16 rounding of W * g
+                    wf = torch.cat([sd[p + '.q.weight'], sd[p + '.kv.weight']], 0).float()
+                    g, b = sd[blk + '.norm1.weight'].float(), sd[blk + '.norm1.bias'].float()
+                    w[p + '.qkv_ln.weight'] = _pack_lin(wf * g[None, :])
+                    w[p + '.qkv_ln.bias'] = (w[p + '.qkv.bias'] + wf @ b).contiguous()
         # global transformer: in_proj split into the (q,k) projection of LN(x)+pos and the v projection of LN(x)
         E = self.arch.dim_embd
         for i in range(self.arch.n_layers):
@@ -211,8 +219,12 @@ class Engine:
         w = self.w
         if C == 256 and self.fuse_ln_qkv:
             # norm1 + the fused q/kv projection in one kernel (LN applied to the tile in shared memory)
-            qkv = ops.ln_linear(x, w[p + '.norm1.weight'], w[p + '.norm1.bias'], w[p + '.attn.qkv.weight'],
-                                w[p + '.attn.qkv.bias'], self._new(Fr, H, W, 3 * C))
+            if (p + '.attn.qkv_ln.weight') in w:      # gamma / beta already inside the weights (see _repack)
+                qkv = ops.ln_linear(x, None, None, w[p + '.attn.qkv_ln.weight'], w[p + '.attn.qkv_ln.bias'],
+                                    self._new(Fr, H, W, 3 * C))
+            else:
+                qkv = ops.ln_linear(x, w[p + '.norm1.weight'], w[p + '.norm1.bias'], w[p + '.attn.qkv.weight'],
+                                    w[p + '.attn.qkv.bias'], self._new(Fr, H, W, 3 * C))
         else:
             y = ops.layernorm(x, w[p + '.norm1.weight'], w[p + '.norm1.bias'], self._new(Fr, H, W, C))
             qkv = self._lin(y, p + '.attn.qkv', 3 * C)
