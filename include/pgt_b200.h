@@ -186,7 +186,8 @@ int pgt_ln_linear_bf16(const void* x, int ldx, int T, int C, const float* ln_g, 
 
 /* ---- fused Swin MLP half-block (C = 256):  out = x + fc2(GELU(fc1(LayerNorm(x)))) in ONE kernel — the hidden tile
  * stays in shared memory / TMEM, x is read once and out written once.  W1, W2: bf16 [C, C] row-major ([out, in]);
- * gn_stats: optional GroupNorm partials of `out` as in pgt_epilogue.  Returns PGT_ERR_UNSUPPORTED for C != 256.
+ * gn_stats: optional GroupNorm partials of `out` as in pgt_epilogue.  ln_g == ln_b == NULL: plain normalisation (the
+ * caller folded gamma / beta into W1 / b1, as for pgt_ln_linear_bf16).  Returns PGT_ERR_UNSUPPORTED for C != 256.
  * Replaces norm2 + Mlp + residual of VSTSREncoderTransformerBlock (modules/rstt_layers.py:116-132,335-336). */
 int pgt_swin_mlp_bf16(const void* x, int ldx, int T, int C, const float* ln_g, const float* ln_b, float eps,
                       const void* W1, const float* b1, const void* W2, const float* b2, void* out, int ldo,

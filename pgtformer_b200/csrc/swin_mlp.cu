@@ -96,14 +96,19 @@ __device__ __forceinline__ void swin_mlp_compute(const SwinMlpParams& p, uint8_t
         const uint4 u = *ptr;
         const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
         const float v[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
-        const int col = kb * 64 + c * 8;
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_g + col)), g1 = __ldg(reinterpret_cast<const float4*>(p.ln_g + col + 4));
-        const float4 e0 = __ldg(reinterpret_cast<const float4*>(p.ln_b + col)), e1 = __ldg(reinterpret_cast<const float4*>(p.ln_b + col + 4));
-        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
         float y[8];
+        if (p.ln_g != nullptr) {
+          const int col = kb * 64 + c * 8;
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_g + col)), g1 = __ldg(reinterpret_cast<const float4*>(p.ln_g + col + 4));
+          const float4 e0 = __ldg(reinterpret_cast<const float4*>(p.ln_b + col)), e1 = __ldg(reinterpret_cast<const float4*>(p.ln_b + col + 4));
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = fmaf(fmaf(v[j], rstd, nm), gg[j], ee[j]);
+          for (int j = 0; j < 8; ++j) y[j] = fmaf(fmaf(v[j], rstd, nm), gg[j], ee[j]);
+        } else {                               // gamma / beta folded into W1 / b1 by the caller
+#pragma unroll
+          for (int j = 0; j < 8; ++j) y[j] = fmaf(v[j], rstd, nm);
+        }
         uint4 o;
         o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
         o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
@@ -314,7 +319,7 @@ using namespace pgt;
 extern "C" int pgt_swin_mlp_bf16(const void* x, int ldx, int T, int C, const float* ln_g, const float* ln_b, float eps,
                                  const void* W1, const float* b1, const void* W2, const float* b2, void* out, int ldo,
                                  float* gn_stats, void* stream) {
-  PGT_CHECK_ARG(x && out && ln_g && ln_b && W1 && W2 && b1 && b2 && T > 0);
+  PGT_CHECK_ARG(x && out && W1 && W2 && b1 && b2 && T > 0 && ((ln_g == nullptr) == (ln_b == nullptr)));   // both null: no affine
   if (C != SM_C) return PGT_ERR_UNSUPPORTED;
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   PGT_CHECK_ARG(al(x) && al(out) && al(W1) && al(W2) && ldx % 8 == 0 && ldo % 8 == 0);

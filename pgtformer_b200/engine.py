@@ -138,6 +138,16 @@ class Engine:
             wi, bi = sd[p + '.in_proj_weight'].float(), sd[p + '.in_proj_bias'].float()
             w[p + '.qk.weight'], w[p + '.qk.bias'] = _pack_lin(wi[:2 * E]), bi[:2 * E].contiguous()
             w[p + '.v.weight'], w[p + '.v.bias'] = _pack_lin(wi[2 * E:]), bi[2 * E:].contiguous()
+        # Swin MLP halves: norm2's affine folded into fc1 (same algebra as norm1 -> q/kv above)
+        if self.fuse_swin_mlp:
+            for name in list(sd):
+                if name.endswith('.mlp.fc1.weight') and sd[name].shape == (256, 256):
+                    blk = name[:-len('.mlp.fc1.weight')]
+                    if (blk + '.norm2.weight') not in sd:
+                        continue
+                    wf, g, b = sd[name].float(), sd[blk + '.norm2.weight'].float(), sd[blk + '.norm2.bias'].float()
+                    w[blk + '.mlp.fc1_ln.weight'] = _pack_lin(wf * g[None, :])
+                    w[blk + '.mlp.fc1_ln.bias'] = (sd[blk + '.mlp.fc1.bias'].float() + wf @ b).contiguous()
         self._repack_parsing()
 
     # ------------------------------------------------------------------ small helpers
@@ -240,6 +250,9 @@ class Engine:
                 tpf = H * W // 128
                 stats = self._new(Fr * tpf * 4 * 64, dtype=torch.float32)
                 out._pgt_gn = (stats, tpf * 4)
+            if (p + '.mlp.fc1_ln.weight') in w:       # gamma / beta already inside fc1 (see _repack)
+                return ops.swin_mlp(x, None, None, w[p + '.mlp.fc1_ln.weight'], w[p + '.mlp.fc1_ln.bias'],
+                                    w[p + '.mlp.fc2.weight'], w[p + '.mlp.fc2.bias'], out, gn_stats=stats)
             return ops.swin_mlp(x, w[p + '.norm2.weight'], w[p + '.norm2.bias'], w[p + '.mlp.fc1.weight'],
                                 w[p + '.mlp.fc1.bias'], w[p + '.mlp.fc2.weight'], w[p + '.mlp.fc2.bias'], out,
                                 gn_stats=stats)
