@@ -9,7 +9,8 @@
 //
 // Per CTA, persistent over 128-token tiles (640 threads):
 //   warp 0        TMA producer of the weight k-blocks (W1 / W2, 256 x 64 each, 3-deep ring shared by both groups)
-//   warp 1        tcgen05.mma issuer for both groups in the fixed order  G1(a) G1(b) G2(a) G2(b);  group g accumulates
+//   warp 1        tcgen05.mma issuer for both groups in the fixed order  G2(b') G1(a) G2(a) G1(b)  (b half a tile behind
+//                 a);  group g accumulates
 //                 in TMEM columns [256 g, 256 g + 256) — GEMM2 reuses GEMM1's columns once the GELU pass has read them
 //   warp 2+g      DMA of group g: TMA load of the x tile, re-fetch of x (an L2 hit) for the residual once GEMM2 has
 //                 consumed the buffer, TMA store of the finished tile
@@ -216,56 +217,61 @@ swin_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int n_loc = (int)blockIdx.x < p.m_tiles ? (p.m_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int n_grp[2] = {(n_loc + 1) >> 1, n_loc >> 1};
 
+  // GEMM order of the CTA (weight producer and MMA issuer walk the same list).  Group b runs half a tile behind group a:
+  //   ... G2(b, i-1)  G1(a, i)  G2(a, i)  G1(b, i)  G2(b, i) ...
+  // so that one group's TMA load / LayerNorm / store phases fall into the other's GEMM + GELU phases.  With the two groups
+  // in phase (G1a G1b G2a G2b) every CTA of the grid loaded, normalised and stored at the same moments, and each x load
+  // queued behind 19 MB of simultaneous requests.
+  auto for_each_gemm = [&](auto&& fn) {
+    for (int it = 0; it < n_grp[0]; ++it) {
+      if (it >= 1 && it - 1 < n_grp[1]) fn(1, 1, it - 1);
+      fn(0, 0, it);
+      fn(1, 0, it);
+      if (it < n_grp[1]) fn(0, 1, it);
+    }
+    if (n_grp[1] >= 1 && n_grp[1] == n_grp[0]) fn(1, 1, n_grp[1] - 1);
+  };
+
   if (warp == 0) {
     // ------------------------------------------------------------------ weight producer (same order as the MMA warp)
     int st = 0;
     uint32_t ph = 0;
-    for (int it = 0; it < n_grp[0]; ++it) {
-      for (int gemm = 0; gemm < 2; ++gemm) {
-        for (int g = 0; g < 2; ++g) {
-          if (it >= n_grp[g]) continue;
-          for (int kb = 0; kb < 4; ++kb) {
-            mbar_wait(&w_empty[st], ph ^ 1);
-            if (elect_one()) {
-              mbar_arrive_expect_tx(&w_full[st], SM_WBYTES);
-              tma_load_2d(sW + st * SM_WBYTES, gemm == 0 ? &tmW1 : &tmW2, &w_full[st], kb * 64, 0);
-            }
-            __syncwarp();
-            if (++st == SM_WST) { st = 0; ph ^= 1; }
-          }
+    for_each_gemm([&](int gemm, int /*g*/, int /*it*/) {
+      for (int kb = 0; kb < 4; ++kb) {
+        mbar_wait(&w_empty[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&w_full[st], SM_WBYTES);
+          tma_load_2d(sW + st * SM_WBYTES, gemm == 0 ? &tmW1 : &tmW2, &w_full[st], kb * 64, 0);
         }
+        __syncwarp();
+        if (++st == SM_WST) { st = 0; ph ^= 1; }
       }
-    }
+    });
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = umma_idesc_bf16(SM_BM, SM_C);
     int st = 0;
     uint32_t ph = 0;
-    for (int it = 0; it < n_grp[0]; ++it) {
+    for_each_gemm([&](int gemm, int g, int it) {
       const uint32_t par = it & 1;
-      for (int gemm = 0; gemm < 2; ++gemm) {
-        for (int g = 0; g < 2; ++g) {
-          if (it >= n_grp[g]) continue;
-          uint8_t* sX = smem + g * 4 * SM_SUB;
-          mbar_wait(gemm == 0 ? &gbar[g].y_ready : &gbar[g].h_ready, par);
-          tc_fence_after();
-          for (int kb = 0; kb < 4; ++kb) {
-            mbar_wait(&w_full[st], ph);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t da = umma_desc_k_sw128(smem_u32(sX + kb * SM_SUB));
-              const uint64_t db = umma_desc_k_sw128(smem_u32(sW + st * SM_WBYTES));
+      uint8_t* sX = smem + g * 4 * SM_SUB;
+      mbar_wait(gemm == 0 ? &gbar[g].y_ready : &gbar[g].h_ready, par);
+      tc_fence_after();
+      for (int kb = 0; kb < 4; ++kb) {
+        mbar_wait(&w_full[st], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t da = umma_desc_k_sw128(smem_u32(sX + kb * SM_SUB));
+          const uint64_t db = umma_desc_k_sw128(smem_u32(sW + st * SM_WBYTES));
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + g * SM_C, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-              umma_commit(&w_empty[st]);
-              if (kb == 3) umma_commit(gemm == 0 ? &gbar[g].acc1_full : &gbar[g].acc2_full);
-            }
-            __syncwarp();
-            if (++st == SM_WST) { st = 0; ph ^= 1; }
-          }
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + g * SM_C, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&w_empty[st]);
+          if (kb == 3) umma_commit(gemm == 0 ? &gbar[g].acc1_full : &gbar[g].acc2_full);
         }
+        __syncwarp();
+        if (++st == SM_WST) { st = 0; ph ^= 1; }
       }
-    }
+    });
   } else if (warp < 4) {
     // ------------------------------------------------------------------ DMA warp of group g
     const int g = warp - 2;
