@@ -7,7 +7,8 @@ each such test says which one:
   * attention kernels (window, MHA), 4e-3: the softmax probabilities P are bf16 operands of the P V tensor-core product
     (relative rounding 2^-9 per element of a convex combination);
   * fused Swin MLP, 4e-3: the GELU(fc1) hidden tile is a bf16 operand of fc2; fused LN + linear, 3e-3: LN(x) is a bf16
-    operand of the projection;
+    operand of the projection; their folded-affine variants (gamma / beta inside the weights), 4e-3 / 6e-3 against the
+    fp32 block with UNROUNDED weights: W * gamma is rounded to bf16 once on top of the above;
   * upsample-folded conv, 6e-3: each 2x2 phase weight is a SUM of up to four 3x3 taps rounded to bf16 once (the oracle
     multiplies the four bf16 taps separately); RGB stem with normalisation, 6e-3: the normalised pixel is rounded to bf16;
   * GroupNorm from fused statistics, 3e-3: the statistics are accumulated from the producer's fp32 accumulators, the
@@ -585,3 +586,39 @@ def test_ln_linear_fused(T, N):
     torch.cuda.synchronize()
     y = bf(F.layer_norm(x.float(), (C,), g, b, 1e-5)).float()
     check_close(out, y @ w.float().t() + wb, 'fused LN + linear', bf16_out=True, rel=3e-3)
+
+@pytest.mark.parametrize('T,N', [(1000, 768), (12288, 256)])
+def test_ln_linear_folded_affine(T, N):
+    """NULL gamma / beta in the C ABI: the caller folded the LayerNorm affine into the weights (W * gamma, bias + W beta),
+    as Engine._repack does for norm1 -> q/kv.  Checked against the fp32 LayerNorm + linear of the UNFOLDED parameters:
+    the folded path rounds W * gamma once instead of rounding LN(x) and W separately, same tolerance."""
+    o = ops()
+    C = 256
+    x = bf(rnd((T, C), 210) * 1.5 + 0.1)
+    g, b = 1 + 0.1 * rnd((C,), 211), 0.1 * rnd((C,), 212)
+    w, wb = rnd((N, C), 213, C ** -0.5), rnd((N,), 214, 0.1)
+    wf = bf(w * g[None, :])
+    bf_ = wb + w @ b
+    out = torch.full((T, N), 9.0, dtype=torch.bfloat16, device=DEV)
+    o.ln_linear(x.to(DEV), None, None, wf.to(DEV), bf_.to(DEV), out)
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x.float(), (C,), g, b, 1e-5) @ w.t() + wb
+    check_close(out, ref, 'LN + linear, affine folded into W', bf16_out=True, rel=4e-3)
+
+
+def test_swin_mlp_folded_affine():
+    """NULL gamma / beta: norm2's affine folded into fc1 (Engine._repack); vs the fp32 composition of the unfolded block."""
+    o = ops()
+    T, C = 1000, 256
+    x = bf(rnd((T, C), 220) * 1.5 + 0.1)
+    g, b = 1 + 0.1 * rnd((C,), 221), 0.1 * rnd((C,), 222)
+    w1, b1 = rnd((C, C), 223, C ** -0.5), rnd((C,), 224, 0.1)
+    w2, b2 = bf(rnd((C, C), 225, C ** -0.5)), rnd((C,), 226, 0.1)
+    w1f, b1f = bf(w1 * g[None, :]), b1 + w1 @ b
+    out = torch.empty(T, C, dtype=torch.bfloat16, device=DEV)
+    o.swin_mlp(x.to(DEV), None, None, w1f.to(DEV), b1f.to(DEV), w2.to(DEV), b2.to(DEV), out)
+    torch.cuda.synchronize()
+    hdn = F.gelu(F.layer_norm(x.float(), (C,), g, b, 1e-5) @ w1.t() + b1)
+    ref = x.float() + hdn @ w2.float().t() + b2
+    check_close(out, ref, 'Swin MLP, affine folded into fc1', bf16_out=True, rel=6e-3)
+
