@@ -10,14 +10,16 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity > gpurun_out/prof/launches_bench.log 2>&1
 gzip -f gpurun_out/prof/launches.csv
 timeout 300 python tools/layer_profile.py 16 512 > gpurun_out/prof/layers.txt 2>&1
+if [ -z "${PGT_PROFILE_SKIP_TRAFFIC:-}" ]; then
 # DRAM traffic of every launch of one forward (roofline.traffic of bench.py: profiles/<tag>_traffic.json)
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -c 6000 --csv \
     --log-file gpurun_out/prof/traffic.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity > gpurun_out/prof/traffic_bench.log 2>&1
 gzip -f gpurun_out/prof/traffic.csv
-for op in halo64 halo128 conv256 linear256 swin_mlp rgb gn window_tc mha_tc argmax l2_argmin ln_linear conv_out; do
+fi
+for op in ${PGT_PROFILE_OPS:-halo64 halo128 conv256 linear256 linear512 linear512_f32 up128 swin_mlp rgb gn window_tc mha_tc argmax l2_argmin ln_linear conv_out}; do
   case $op in
-    halo64|halo128) rx='regex:conv_halo' ;;
-    conv256|linear256) rx='regex:gemm_tc_kernel' ;;
+    halo64|halo128|up128) rx='regex:conv_halo' ;;
+    conv256|linear256|linear512|linear512_f32) rx='regex:gemm_tc_kernel' ;;
     swin_mlp) rx='regex:swin_mlp' ;;
     rgb) rx='regex:rgb_conv' ;;
     gn) rx='regex:gn_apply' ;;

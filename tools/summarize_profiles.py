@@ -104,6 +104,9 @@ OPS = [('window_tc', 'window_attn_tc_kernel<32>: 4 clips x 1024 shifted windows 
        ('halo128', 'conv_halo2_kernel<128> (CTA pairs): 3x3, 12 frames 256^2, Cin=Cout=128, residual'),
        ('conv256', 'gemm_tc_kernel<256, pair>: 3x3, 12 frames 128^2, Cin=Cout=256 (K=2304), residual'),
        ('linear256', 'gemm_tc_kernel<256>: linear M=196608 N=256 K=256 + residual (HBM / L2 bound)'),
+       ('linear512', 'gemm_tc_kernel<256>: linear M=49152 N=512 K=512 + bf16 residual (the 32^2-level Swin / global-transformer shape)'),
+       ('linear512_f32', 'gemm_tc_kernel<256>: linear M=49152 N=512 K=512 + fp32 residual stream (global transformer out_proj / linear2)'),
+       ('up128', 'conv_halo_kernel<128>: one 2x2 phase conv of the folded Upsample, 12 frames 256^2 -> 512^2, Cin=Cout=128'),
        ('swin_mlp', 'swin_mlp_kernel: LN+fc1+GELU+fc2+residual, T=196608, C=256'),
        ('rgb', 'rgb_conv_kernel<3,1,1>: conv_in 3->64 on 12 frames 512^2 with GroupNorm statistics'),
        ('gn', 'gn_apply_kernel (last of stats/finalize/apply): GroupNorm+SiLU, 12 frames 512^2 x 64')]
