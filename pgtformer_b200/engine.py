@@ -44,6 +44,15 @@ def _pack_conv(w):
     return wp.reshape(co, kh * kw * cp).to(BF).contiguous()
 
 
+def fold_layernorm_affine(weight, bias, gamma, beta):
+    """(x_hat * gamma + beta) W^T + c  ==  x_hat (W * gamma)^T + (W beta + c), x_hat = (x - mean) * rstd: the affine of a
+    LayerNorm folded into the linear layer that consumes it (norm1 -> q/kv and norm2 -> fc1 of the C = 256 Swin blocks,
+    `modules/rstt_layers.py:298-336`), so that the fused kernels only normalise.  fp32 in, fp32 out (the caller rounds the
+    folded weight to bf16 once).  Returns (W * gamma [N, C], W beta + c [N])."""
+    wf = weight.float()
+    return wf * gamma.float()[None, :], (bias.float() + wf @ beta.float()).contiguous()
+
+
 def _pack_up2x(w):
     """OIHW 3x3 fp32 -> [4, Cout, 4*CinPad] bf16 phase weights of the upsample-folded conv (include/pgt_b200.h):
     phase (py,px), tap (ty,tx) = sum of w[dy,dx] over dy in S(py,ty), dx in S(px,tx); sums in fp32, one bf16 rounding."""
@@ -127,10 +136,9 @@ class Engine:
                 if self.fuse_ln_qkv and sd[p + '.q.weight'].shape[1] == 256 and (blk + '.norm1.weight') in sd:
                     # norm1's affine folded into the projection the fused kernel applies to the normalised tile:
                     # (xh * g + b) W^T + c = xh (W * g)^T + (W b + c); products and sums in fp32, one bf16 rounding of W * g
-                    wf = torch.cat([sd[p + '.q.weight'], sd[p + '.kv.weight']], 0).float()
-                    g, b = sd[blk + '.norm1.weight'].float(), sd[blk + '.norm1.bias'].float()
-                    w[p + '.qkv_ln.weight'] = _pack_lin(wf * g[None, :])
-                    w[p + '.qkv_ln.bias'] = (w[p + '.qkv.bias'] + wf @ b).contiguous()
+                    wf = torch.cat([sd[p + '.q.weight'], sd[p + '.kv.weight']], 0)
+                    wg, bg = fold_layernorm_affine(wf, w[p + '.qkv.bias'], sd[blk + '.norm1.weight'], sd[blk + '.norm1.bias'])
+                    w[p + '.qkv_ln.weight'], w[p + '.qkv_ln.bias'] = _pack_lin(wg), bg
         # global transformer: in_proj split into the (q,k) projection of LN(x)+pos and the v projection of LN(x)
         E = self.arch.dim_embd
         for i in range(self.arch.n_layers):
@@ -145,9 +153,9 @@ class Engine:
                     blk = name[:-len('.mlp.fc1.weight')]
                     if (blk + '.norm2.weight') not in sd:
                         continue
-                    wf, g, b = sd[name].float(), sd[blk + '.norm2.weight'].float(), sd[blk + '.norm2.bias'].float()
-                    w[blk + '.mlp.fc1_ln.weight'] = _pack_lin(wf * g[None, :])
-                    w[blk + '.mlp.fc1_ln.bias'] = (sd[blk + '.mlp.fc1.bias'].float() + wf @ b).contiguous()
+                    wg, bg = fold_layernorm_affine(sd[name], sd[blk + '.mlp.fc1.bias'], sd[blk + '.norm2.weight'],
+                                                   sd[blk + '.norm2.bias'])
+                    w[blk + '.mlp.fc1_ln.weight'], w[blk + '.mlp.fc1_ln.bias'] = _pack_lin(wg), bg
         self._repack_parsing()
 
     # ------------------------------------------------------------------ small helpers
